@@ -1,0 +1,57 @@
+"""Pin the CPU oracle (oracle/oracle.c) bit-for-bit against outputs of the unmodified reference.
+
+The fixtures under tests/golden/ were produced by oracle/gen_models.cpp linked against the
+reference itself: outputs of f.map(N,"serial") (casadi/core/map.cpp:141-157) on seeded inputs.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from casadi_b200.tapeio import load_case, load_tape
+
+SX_CASES = [("cartpole", "cartpole"), ("cartpole1", "cartpole1"), ("quad", "quad"), ("quad1", "quad1"),
+            ("quad_fwd", "quad_fwd"), ("quad_adj", "quad_adj"), ("quad_jac", "quad_jac"),
+            ("quad1_jac", "quad1_jac"), ("rocket_hess", "rocket_hess"), ("mcstep", "mcstep"), ("mc", "mc"),
+            ("mapnode", "mapnode"), ("opcover", "opcover"), ("opcover", "opcover_special")]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+def assert_bit_equal(got, want, what=""):
+    g, w = bits(got), bits(want)
+    same = (g == w) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), "%s: %d/%d values differ (first at %d: %r vs %r)" % (
+        what, (~same).sum(), same.size, np.argmax(~same), got[np.argmax(~same)], want[np.argmax(~same)])
+
+
+@pytest.mark.parametrize("tape_name,case_name", SX_CASES)
+def test_oracle_matches_reference_serial_map(tape_name, case_name):
+    tape = load_tape(tape_name)
+    case = load_case(case_name)
+    outs = oracle.map_eval(tape, case["N"], case["in"])
+    for j, (got, want) in enumerate(zip(outs, case["out"])):
+        assert_bit_equal(got, want, "%s out%d" % (case_name, j))
+
+
+def test_oracle_null_input_reads_zero_and_null_output_skipped():
+    tape = load_tape("mapnode")
+    case = load_case("mapnode")
+    N = case["N"]
+    ins = list(case["in"])
+    zero = [np.zeros_like(a) for a in ins]
+    full = oracle.map_eval(tape, N, [ins[0], zero[1], ins[2], ins[3]])
+    part = oracle.map_eval(tape, N, [ins[0], None, ins[2], ins[3]], want=[True, False, True])
+    assert part[1] is None
+    assert_bit_equal(part[0], full[0])
+    assert_bit_equal(part[2], full[2])
+
+
+def test_oracle_repsum_matches_reference_mapsum():
+    tape = load_tape("mc")
+    case = load_case("mc")
+    ref = load_case("mc_sum")
+    outs = oracle.map_eval(tape, case["N"], case["in"])
+    assert_bit_equal(oracle.repsum(outs[0], 4, case["N"]), ref["out"][0], "sum xT")
+    assert_bit_equal(oracle.repsum(outs[1], 1, case["N"]), ref["out"][1], "sum J")
