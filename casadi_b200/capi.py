@@ -1,0 +1,100 @@
+"""ctypes binding of libcasadi_cuda.so (include/casadi_cuda.h).
+
+The product path: everything here calls the CUDA library through its C ABI.  There is no CPU
+fallback -- if the shared library is missing, or no CUDA device is present, the calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libcasadi_cuda.so")
+
+c_ll = ctypes.c_longlong
+c_ll_p = ctypes.POINTER(ctypes.c_longlong)
+c_i_p = ctypes.POINTER(ctypes.c_int)
+c_d_p = ctypes.POINTER(ctypes.c_double)
+c_vp = ctypes.c_void_p
+
+LAYOUT_AOS = 0
+LAYOUT_SOA = 1
+
+# every symbol include/casadi_cuda.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "ccu_abi_version": (ctypes.c_int, []),
+    "ccu_last_error": (ctypes.c_char_p, []),
+    "ccu_device_count": (ctypes.c_int, []),
+    "ccu_tape_create": (c_vp, [c_ll, c_i_p, c_i_p, c_i_p, c_i_p, c_d_p, c_ll, c_ll, c_ll_p, c_ll, c_ll_p,
+                               ctypes.c_int]),
+    "ccu_tape_destroy": (None, [c_vp]),
+    "ccu_tape_get_info": (ctypes.c_int, [c_vp, c_vp]),
+    "ccu_tape_get_program": (c_ll, [c_vp, c_vp, c_ll]),
+    "ccu_tape_set_plan": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "ccu_map_eval_host": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp]),
+    "ccu_map_eval_device": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, ctypes.c_int, c_vp]),
+    "ccu_map_eval_reduce_host": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_i_p, c_i_p]),
+    "ccu_map_eval_reduce_device": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_i_p, c_i_p, ctypes.c_int, c_vp]),
+    "ccu_tape_last_kernel_ms": (ctypes.c_int, [c_vp, c_d_p]),
+    "ccu_launch_count": (c_ll, []),
+    "ccu_set_device": (ctypes.c_int, [ctypes.c_int]),
+    "ccu_malloc": (c_vp, [c_ll]),
+    "ccu_free": (ctypes.c_int, [c_vp]),
+    "ccu_malloc_host": (c_vp, [c_ll]),
+    "ccu_free_host": (ctypes.c_int, [c_vp]),
+    "ccu_memcpy_h2d": (ctypes.c_int, [c_vp, c_vp, c_ll, c_vp]),
+    "ccu_memcpy_d2h": (ctypes.c_int, [c_vp, c_vp, c_ll, c_vp]),
+    "ccu_stream_sync": (ctypes.c_int, [c_vp]),
+    "ccu_device_sync": (ctypes.c_int, []),
+}
+
+
+class TapeInfo(ctypes.Structure):
+    _fields_ = [(n, c_ll) for n in ("n_instr", "n_words", "flops", "bytes_in", "bytes_out", "sz_w", "slots_shared",
+                                    "slots_global", "threads", "ipt", "smem_bytes", "spill_loads", "spill_stores",
+                                    "max_live", "grid", "ctas_per_sm")]
+
+
+_lib = None
+
+
+class CcuError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CcuError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().ccu_last_error().decode()
+
+
+def check(rc):
+    if rc != 0:
+        raise CcuError(last_error())
+
+
+def ptr_array(ptrs):
+    """(void*)[n] from ints/None."""
+    n = max(len(ptrs), 1)
+    return (ctypes.c_void_p * n)(*[None if (p is None or p == 0) else int(p) for p in ptrs])
+
+
+def int_array(vals):
+    if vals is None:
+        return None
+    a = np.ascontiguousarray([1 if v else 0 for v in vals], np.int32)
+    return a

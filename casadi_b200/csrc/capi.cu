@@ -1,0 +1,428 @@
+// C ABI of libcasadi_cuda.so (include/casadi_cuda.h): handle management, plan selection,
+// host- and device-pointer evaluation paths.  No CPU fallback anywhere: every evaluation entry
+// point fails when the tape has no CUDA device.
+#include "../../include/casadi_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ccu_isa.h"
+#include "interp.cuh"
+#include "reduce.cuh"
+#include "tape_compile.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define CCU_CUDA(call)                                                                        \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                       __FILE__, __LINE__);                                   \
+  } while (0)
+
+struct DevBuf {
+  double* p = nullptr;
+  size_t cap = 0;  // doubles
+  int ensure(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 1024;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(double));
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, n * sizeof(double));
+      want = n;
+    }
+    if (e != cudaSuccess) return fail("cudaMalloc of %zu bytes failed: %s", n * sizeof(double), cudaGetErrorString(e));
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct ccu_tape {
+  int device = -1;
+  // source tape (kept for re-planning)
+  std::vector<int> op, i0, i1, i2;
+  std::vector<double> d;
+  long long sz_w = 0;
+  std::vector<long long> nnz_in, nnz_out;
+  long long max_live = 0, flops = 0;
+  // compiled program + plan
+  ccu::Program prog;
+  ccu::LaunchPlan plan;
+  bool use_acc = true;
+  uint64_t* d_prog = nullptr;
+  DevBuf scratch;
+  // staging for the host-pointer path
+  std::vector<DevBuf> d_in, d_out, d_part;
+  DevBuf d_tmp;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+
+  ccu::TapeSource source() const {
+    ccu::TapeSource s;
+    s.n_instr = static_cast<long long>(op.size());
+    s.op = op.data(); s.i0 = i0.data(); s.i1 = i1.data(); s.i2 = i2.data(); s.d = d.data();
+    s.sz_w = sz_w; s.nnz_in = nnz_in; s.nnz_out = nnz_out;
+    return s;
+  }
+};
+
+namespace {
+
+// compile the program for (threads, ipt, S) and upload it
+int build_plan(ccu_tape* t, int threads, int ipt, int slots_shared) {
+  ccu::CompileOptions opt;
+  opt.use_acc = t->use_acc;
+  // automatic choice: keep the whole work vector in shared memory when it is small; otherwise a
+  // fixed shared window and SPILL/FILL to the global scratch
+  if (slots_shared <= 0) slots_shared = t->max_live + 1 <= 96 ? static_cast<int>(t->max_live + 1) : 48;
+  if (slots_shared < 4) slots_shared = 4;
+  opt.slots_shared = slots_shared;
+  std::string err;
+  ccu::Program prog;
+  if (!ccu::compile_tape(t->source(), opt, &prog, &err)) return fail("tape compile failed: %s", err.c_str());
+  if (threads <= 0) threads = 128;
+  if (ipt <= 0) {
+    // two lanes per thread when that still leaves >= 4 CTAs per SM worth of shared memory
+    size_t per_lane = static_cast<size_t>(prog.slots_shared) * 8;
+    ipt = (per_lane * threads * 2 * 4 <= 200 * 1024) ? 2 : 1;
+  }
+  if (threads % 32 != 0 || threads > 1024) return fail("plan: threads must be a multiple of 32, <= 1024");
+  if (ipt != 1 && ipt != 2 && ipt != 4) return fail("plan: ipt must be 1, 2 or 4");
+  ccu::LaunchPlan plan;
+  plan.threads = threads; plan.ipt = ipt;
+  plan.slots_shared = prog.slots_shared; plan.slots_global = prog.slots_global;
+  plan.smem_bytes = static_cast<size_t>(plan.slots_shared) * ipt * threads * sizeof(double);
+  if (plan.smem_bytes > 227 * 1024) return fail("plan needs %zu bytes of shared memory per CTA (> 227 KB)", plan.smem_bytes);
+  if (t->device >= 0) {
+    CCU_CUDA(cudaSetDevice(t->device));
+    cudaError_t e = ccu::plan_occupancy(&plan, t->device);
+    if (e != cudaSuccess) return fail("plan_occupancy: %s", cudaGetErrorString(e));
+    if (t->d_prog) { cudaFree(t->d_prog); t->d_prog = nullptr; }
+    std::vector<uint64_t> padded(prog.words);
+    padded.push_back(ccu::enc(ccu::D_END, 0, 0, 0));
+    padded.push_back(ccu::enc(ccu::D_END, 0, 0, 0));
+    CCU_CUDA(cudaMalloc(&t->d_prog, padded.size() * 8));
+    CCU_CUDA(cudaMemcpy(t->d_prog, padded.data(), padded.size() * 8, cudaMemcpyHostToDevice));
+  }
+  t->prog = std::move(prog);
+  t->plan = plan;
+  return 0;
+}
+
+int ensure_scratch(ccu_tape* t) {
+  if (t->plan.slots_global == 0) return 0;
+  size_t n = static_cast<size_t>(t->plan.slots_global) * t->plan.grid * t->plan.threads * t->plan.ipt;
+  return t->scratch.ensure(n);
+}
+
+int launch(ccu_tape* t, const ccu::IoDesc& io, long long N, cudaStream_t stream) {
+  if (ensure_scratch(t)) return 1;
+  if (t->ev0) cudaEventRecord(t->ev0, stream);
+  cudaError_t e = ccu::launch_interp(t->plan, t->d_prog, io, N, t->scratch.p, stream);
+  if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
+  if (t->ev1) cudaEventRecord(t->ev1, stream);
+  t->timed = true;
+  if (N > 0) g_launches++;
+  return 0;
+}
+
+int check_eval_args(const ccu_tape* t, long long N) {
+  if (!t) return fail("null tape");
+  if (t->device < 0) return fail("tape was compiled without a CUDA device: evaluation impossible (no CPU fallback)");
+  if (N < 0) return fail("negative batch size");
+  if (t->nnz_in.size() > ccu::kMaxIO || t->nnz_out.size() > ccu::kMaxIO)
+    return fail("more than %d inputs or outputs are not supported", ccu::kMaxIO);
+  return 0;
+}
+
+void fill_io(const ccu_tape* t, long long N, const double* const* d_arg, double* const* d_res, int layout,
+             const int* reduce_in, ccu::IoDesc* io) {
+  std::memset(io, 0, sizeof(*io));
+  for (size_t j = 0; j < t->nnz_in.size(); ++j) {
+    io->in[j] = t->nnz_in[j] > 0 ? d_arg[j] : nullptr;
+    if (reduce_in && reduce_in[j]) { io->in_si[j] = 0; io->in_sk[j] = 1; }
+    else if (layout == CCU_LAYOUT_SOA) { io->in_si[j] = 1; io->in_sk[j] = N; }
+    else { io->in_si[j] = t->nnz_in[j]; io->in_sk[j] = 1; }
+  }
+  for (size_t j = 0; j < t->nnz_out.size(); ++j) {
+    io->out[j] = t->nnz_out[j] > 0 ? d_res[j] : nullptr;
+    if (layout == CCU_LAYOUT_SOA) { io->out_si[j] = 1; io->out_sk[j] = N; }
+    else { io->out_si[j] = t->nnz_out[j]; io->out_sk[j] = 1; }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ccu_abi_version(void) { return CCU_ABI_VERSION; }
+const char* ccu_last_error(void) { return g_err.c_str(); }
+
+int ccu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+ccu_tape* ccu_tape_create(ccu_int n_instr, const int* op, const int* i0, const int* i1, const int* i2,
+                          const double* d, ccu_int sz_w, ccu_int n_in, const ccu_int* nnz_in, ccu_int n_out,
+                          const ccu_int* nnz_out, int device) {
+  if (n_instr < 0 || n_in < 0 || n_out < 0 || (n_instr > 0 && (!op || !i0 || !i1 || !i2 || !d)) ||
+      (n_in > 0 && !nnz_in) || (n_out > 0 && !nnz_out)) {
+    fail("ccu_tape_create: invalid arguments");
+    return nullptr;
+  }
+  ccu_tape* t = new ccu_tape();
+  t->op.assign(op, op + n_instr); t->i0.assign(i0, i0 + n_instr); t->i1.assign(i1, i1 + n_instr);
+  t->i2.assign(i2, i2 + n_instr); t->d.assign(d, d + n_instr);
+  t->sz_w = sz_w;
+  t->nnz_in.assign(nnz_in, nnz_in + n_in);
+  t->nnz_out.assign(nnz_out, nnz_out + n_out);
+  const char* noacc = getenv("CCU_NO_ACC");
+  t->use_acc = !(noacc && noacc[0] == '1');
+  std::string err;
+  if (!ccu::analyse_tape(t->source(), &t->max_live, &t->flops, &err)) {
+    fail("invalid tape: %s", err.c_str());
+    delete t;
+    return nullptr;
+  }
+  if (device >= 0) {
+    int n = ccu_device_count();
+    if (device >= n) {
+      fail("CUDA device %d not available (%d device(s) visible); there is no CPU fallback", device, n);
+      delete t;
+      return nullptr;
+    }
+    t->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&t->ev0) != cudaSuccess || cudaEventCreate(&t->ev1) != cudaSuccess) {
+      fail("CUDA initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      delete t;
+      return nullptr;
+    }
+  }
+  int threads = 0, ipt = 0, S = 0;
+  if (const char* p = getenv("CCU_PLAN")) sscanf(p, "%d,%d,%d", &threads, &ipt, &S);
+  if (build_plan(t, threads, ipt, S)) {
+    ccu_tape_destroy(t);
+    return nullptr;
+  }
+  t->d_in.resize(n_in); t->d_out.resize(n_out); t->d_part.resize(n_out);
+  return t;
+}
+
+void ccu_tape_destroy(ccu_tape* t) {
+  if (!t) return;
+  if (t->device >= 0) {
+    cudaSetDevice(t->device);
+    if (t->d_prog) cudaFree(t->d_prog);
+    t->scratch.release(); t->d_tmp.release();
+    for (auto& b : t->d_in) b.release();
+    for (auto& b : t->d_out) b.release();
+    for (auto& b : t->d_part) b.release();
+    if (t->ev0) cudaEventDestroy(t->ev0);
+    if (t->ev1) cudaEventDestroy(t->ev1);
+    if (t->stream) cudaStreamDestroy(t->stream);
+  }
+  delete t;
+}
+
+int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info) {
+  if (!t || !info) return fail("null argument");
+  std::memset(info, 0, sizeof(*info));
+  info->n_instr = t->prog.n_instr;
+  info->n_words = static_cast<ccu_int>(t->prog.words.size());
+  info->flops = t->flops;
+  for (auto v : t->nnz_in) info->bytes_in += 8 * v;
+  for (auto v : t->nnz_out) info->bytes_out += 8 * v;
+  info->sz_w = t->sz_w;
+  info->slots_shared = t->plan.slots_shared;
+  info->slots_global = t->plan.slots_global;
+  info->threads = t->plan.threads;
+  info->ipt = t->plan.ipt;
+  info->smem_bytes = static_cast<ccu_int>(t->plan.smem_bytes);
+  info->spill_loads = t->prog.spill_loads;
+  info->spill_stores = t->prog.spill_stores;
+  info->reserved[0] = t->max_live;
+  info->reserved[1] = t->plan.grid;
+  info->reserved[2] = t->plan.ctas_per_sm;
+  return 0;
+}
+
+int ccu_tape_set_plan(ccu_tape* t, int threads, int ipt, int slots_shared) {
+  if (!t) return fail("null tape");
+  return build_plan(t, threads, ipt, slots_shared);
+}
+
+ccu_int ccu_tape_get_program(const ccu_tape* t, unsigned long long* words, ccu_int cap) {
+  if (!t) { fail("null tape"); return -1; }
+  ccu_int n = static_cast<ccu_int>(t->prog.words.size());
+  if (words) std::memcpy(words, t->prog.words.data(), 8 * static_cast<size_t>(n < cap ? n : cap));
+  return n;
+}
+
+int ccu_map_eval_device(ccu_tape* t, ccu_int N, const double* const* d_arg, double* const* d_res, int layout,
+                        void* stream) {
+  if (check_eval_args(t, N)) return 1;
+  if (layout != CCU_LAYOUT_AOS && layout != CCU_LAYOUT_SOA) return fail("unknown layout %d", layout);
+  if (N == 0) return 0;
+  CCU_CUDA(cudaSetDevice(t->device));
+  ccu::IoDesc io;
+  fill_io(t, N, d_arg, d_res, layout, nullptr, &io);
+  return launch(t, io, N, static_cast<cudaStream_t>(stream));
+}
+
+int ccu_map_eval_reduce_device(ccu_tape* t, ccu_int N, const double* const* d_arg, double* const* d_res,
+                               const int* reduce_in, const int* reduce_out, int layout, void* stream_) {
+  if (check_eval_args(t, N)) return 1;
+  if (layout != CCU_LAYOUT_AOS && layout != CCU_LAYOUT_SOA) return fail("unknown layout %d", layout);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CCU_CUDA(cudaSetDevice(t->device));
+  const size_t n_out = t->nnz_out.size();
+  // reduced outputs are first evaluated per instance into a temporary (SoA), then tree-summed
+  std::vector<double*> res(n_out);
+  for (size_t j = 0; j < n_out; ++j) {
+    res[j] = d_res[j];
+    if (reduce_out && reduce_out[j] && d_res[j] && t->nnz_out[j] > 0) {
+      if (t->d_out[j].ensure(static_cast<size_t>(N) * t->nnz_out[j])) return 1;
+      res[j] = t->d_out[j].p;
+    }
+  }
+  ccu::IoDesc io;
+  fill_io(t, N, d_arg, res.data(), layout, reduce_in, &io);
+  if (N > 0 && launch(t, io, N, stream)) return 1;
+  const long long nblocks = (N + ccu::kReduceBlock - 1) / ccu::kReduceBlock;
+  for (size_t j = 0; j < n_out; ++j) {
+    if (!(reduce_out && reduce_out[j] && d_res[j] && t->nnz_out[j] > 0)) continue;
+    const int nnz = static_cast<int>(t->nnz_out[j]);
+    if (t->d_part[j].ensure(static_cast<size_t>(nblocks > 0 ? nblocks : 1) * nnz)) return 1;
+    CCU_CUDA(ccu::launch_block_sums(res[j], io.out_si[j], io.out_sk[j], N, nnz, t->d_part[j].p, stream));
+    CCU_CUDA(ccu::launch_tree(t->d_part[j].p, nblocks, nnz, d_res[j], stream));
+    g_launches += (N > 0 ? 2 : 1);
+  }
+  return 0;
+}
+
+static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res,
+                          const int* reduce_in, const int* reduce_out) {
+  if (check_eval_args(t, N)) return 1;
+  CCU_CUDA(cudaSetDevice(t->device));
+  const size_t n_in = t->nnz_in.size(), n_out = t->nnz_out.size();
+  std::vector<const double*> d_arg(n_in, nullptr);
+  std::vector<double*> d_res(n_out, nullptr);
+  cudaStream_t s = t->stream;
+  for (size_t j = 0; j < n_in; ++j) {
+    if (!arg[j] || t->nnz_in[j] == 0) continue;
+    size_t cnt = static_cast<size_t>(t->nnz_in[j]) * ((reduce_in && reduce_in[j]) ? 1 : N);
+    if (cnt == 0) continue;
+    if (t->d_in[j].ensure(cnt)) return 1;
+    CCU_CUDA(cudaMemcpyAsync(t->d_in[j].p, arg[j], cnt * 8, cudaMemcpyHostToDevice, s));
+    d_arg[j] = t->d_in[j].p;
+  }
+  std::vector<DevBuf> red(n_out);
+  for (size_t j = 0; j < n_out; ++j) {
+    if (!res[j] || t->nnz_out[j] == 0) continue;
+    const bool r = reduce_out && reduce_out[j];
+    size_t cnt = static_cast<size_t>(t->nnz_out[j]) * (r ? 1 : N);
+    if (cnt == 0) continue;
+    if (r) {
+      if (red[j].ensure(cnt)) return 1;
+      d_res[j] = red[j].p;
+    } else {
+      if (t->d_out[j].ensure(cnt)) return 1;
+      d_res[j] = t->d_out[j].p;
+    }
+  }
+  int rc;
+  if (reduce_in || reduce_out)
+    rc = ccu_map_eval_reduce_device(t, N, d_arg.data(), d_res.data(), reduce_in, reduce_out, CCU_LAYOUT_AOS, s);
+  else
+    rc = ccu_map_eval_device(t, N, d_arg.data(), d_res.data(), CCU_LAYOUT_AOS, s);
+  if (rc == 0) {
+    for (size_t j = 0; j < n_out && rc == 0; ++j) {
+      if (!d_res[j]) continue;
+      size_t cnt = static_cast<size_t>(t->nnz_out[j]) * ((reduce_out && reduce_out[j]) ? 1 : N);
+      cudaError_t e = cudaMemcpyAsync(res[j], d_res[j], cnt * 8, cudaMemcpyDeviceToHost, s);
+      if (e != cudaSuccess) rc = fail("D2H copy failed: %s", cudaGetErrorString(e));
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  for (auto& b : red) b.release();
+  if (rc == 0 && e != cudaSuccess) rc = fail("evaluation failed on device: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+int ccu_map_eval_host(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res) {
+  return eval_host_impl(t, N, arg, res, nullptr, nullptr);
+}
+
+int ccu_map_eval_reduce_host(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res,
+                             const int* reduce_in, const int* reduce_out) {
+  return eval_host_impl(t, N, arg, res, reduce_in, reduce_out);
+}
+
+int ccu_tape_last_kernel_ms(ccu_tape* t, double* ms) {
+  if (!t || !ms) return fail("null argument");
+  if (!t->timed) return fail("no kernel has been launched yet");
+  CCU_CUDA(cudaEventSynchronize(t->ev1));
+  float f = 0;
+  CCU_CUDA(cudaEventElapsedTime(&f, t->ev0, t->ev1));
+  *ms = f;
+  return 0;
+}
+
+ccu_int ccu_launch_count(void) { return g_launches.load(); }
+
+int ccu_set_device(int device) { CCU_CUDA(cudaSetDevice(device)); return 0; }
+void* ccu_malloc(ccu_int bytes) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, static_cast<size_t>(bytes));
+  if (e != cudaSuccess) { fail("cudaMalloc(%lld) failed: %s", bytes, cudaGetErrorString(e)); return nullptr; }
+  return p;
+}
+int ccu_free(void* p) { CCU_CUDA(cudaFree(p)); return 0; }
+void* ccu_malloc_host(ccu_int bytes) {
+  void* p = nullptr;
+  cudaError_t e = cudaMallocHost(&p, static_cast<size_t>(bytes));
+  if (e != cudaSuccess) { fail("cudaMallocHost(%lld) failed: %s", bytes, cudaGetErrorString(e)); return nullptr; }
+  return p;
+}
+int ccu_free_host(void* p) { CCU_CUDA(cudaFreeHost(p)); return 0; }
+int ccu_memcpy_h2d(void* dst, const void* src, ccu_int bytes, void* stream) {
+  CCU_CUDA(cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int ccu_memcpy_d2h(void* dst, const void* src, ccu_int bytes, void* stream) {
+  CCU_CUDA(cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int ccu_stream_sync(void* stream) { CCU_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream))); return 0; }
+int ccu_device_sync(void) { CCU_CUDA(cudaDeviceSynchronize()); return 0; }
+
+}  // extern "C"

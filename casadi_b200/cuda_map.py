@@ -1,0 +1,139 @@
+"""Python mirror of the reference's Map interface for the "cuda" parallelization.
+
+`CudaTape` wraps an exported SXFunction tape (the `f` of `f.map(N, "cuda")`); `CudaMap` mirrors
+casadi::Map (casadi/core/map.hpp:50-170): same argument meaning (AoS host buffers, None = NULL
+argument/result) and error behaviour (exceptions carry the library's message).  All computation is
+in libcasadi_cuda.so; this file only marshals pointers.
+"""
+import ctypes
+
+import numpy as np
+
+from . import capi
+from .capi import CcuError, LAYOUT_AOS, LAYOUT_SOA  # noqa: F401
+
+
+class CudaTape:
+    """A compiled SX tape resident on one device (ccu_tape)."""
+
+    def __init__(self, tape, device=0):
+        L = capi.lib()
+        self.nnz_in = [int(v) for v in tape["nnz_in"]]
+        self.nnz_out = [int(v) for v in tape["nnz_out"]]
+        op = np.ascontiguousarray(tape["op"], np.int32)
+        i0 = np.ascontiguousarray(tape["i0"], np.int32)
+        i1 = np.ascontiguousarray(tape["i1"], np.int32)
+        i2 = np.ascontiguousarray(tape["i2"], np.int32)
+        d = np.ascontiguousarray(tape["d"], np.float64)
+        nin = np.ascontiguousarray(self.nnz_in, np.int64)
+        nout = np.ascontiguousarray(self.nnz_out, np.int64)
+        p = lambda a, t: a.ctypes.data_as(t)  # noqa: E731
+        self.handle = L.ccu_tape_create(len(op), p(op, capi.c_i_p), p(i0, capi.c_i_p), p(i1, capi.c_i_p),
+                                        p(i2, capi.c_i_p), p(d, capi.c_d_p), int(tape["sz_w"]), len(nin),
+                                        p(nin, capi.c_ll_p), len(nout), p(nout, capi.c_ll_p), int(device))
+        if not self.handle:
+            raise CcuError(capi.last_error())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            capi.lib().ccu_tape_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_in(self):
+        return len(self.nnz_in)
+
+    @property
+    def n_out(self):
+        return len(self.nnz_out)
+
+    def info(self):
+        inf = capi.TapeInfo()
+        capi.check(capi.lib().ccu_tape_get_info(self.handle, ctypes.byref(inf)))
+        return {n: int(getattr(inf, n)) for n, _ in inf._fields_}
+
+    def set_plan(self, threads=0, ipt=0, slots_shared=0):
+        capi.check(capi.lib().ccu_tape_set_plan(self.handle, threads, ipt, slots_shared))
+
+    def program(self):
+        L = capi.lib()
+        n = L.ccu_tape_get_program(self.handle, None, 0)
+        words = np.zeros(n, np.uint64)
+        L.ccu_tape_get_program(self.handle, words.ctypes.data, n)
+        return words
+
+    def last_kernel_ms(self):
+        ms = ctypes.c_double()
+        capi.check(capi.lib().ccu_tape_last_kernel_ms(self.handle, ctypes.byref(ms)))
+        return ms.value
+
+    # -- device-pointer evaluation (roofline path) --------------------------------------------------
+    def eval_device(self, N, d_arg, d_res, layout=LAYOUT_SOA, stream=0, reduce_in=None, reduce_out=None):
+        """d_arg/d_res: device addresses (int) or None."""
+        L = capi.lib()
+        a, r = capi.ptr_array(d_arg), capi.ptr_array(d_res)
+        if reduce_in is None and reduce_out is None:
+            capi.check(L.ccu_map_eval_device(self.handle, N, a, r, layout, stream or None))
+        else:
+            ri, ro = capi.int_array(reduce_in), capi.int_array(reduce_out)
+            capi.check(L.ccu_map_eval_reduce_device(
+                self.handle, N, a, r, None if ri is None else ri.ctypes.data_as(capi.c_i_p),
+                None if ro is None else ro.ctypes.data_as(capi.c_i_p), layout, stream or None))
+
+
+class CudaMap:
+    """f.map(N, "cuda"): evaluates the tape for N instances; host buffers in the reference's layout
+    (instance i of input j = arg[j][i*nnz_in[j] : (i+1)*nnz_in[j]], casadi/core/map.cpp:149-154)."""
+
+    def __init__(self, tape, n, device=0, reduce_in=None, reduce_out=None):
+        if n <= 0:
+            raise CcuError("Degenerate map operation")  # function.cpp:862
+        self.f = tape if isinstance(tape, CudaTape) else CudaTape(tape, device)
+        self.n = int(n)
+        self.reduce_in = list(reduce_in) if reduce_in is not None else None
+        self.reduce_out = list(reduce_out) if reduce_out is not None else None
+
+    def parallelization(self):
+        return "cuda"
+
+    def __call__(self, args, want=None):
+        """args[j]: float64 array (n*nnz_in[j] values, AoS) or None.  Returns list of arrays (None where
+        want[j] is False)."""
+        f, N = self.f, self.n
+        if len(args) != f.n_in:
+            raise CcuError("expected %d inputs, got %d" % (f.n_in, len(args)))
+        ins = []
+        for j, a in enumerate(args):
+            if a is None:
+                ins.append(None)
+                continue
+            a = np.ascontiguousarray(a, np.float64).ravel()
+            cnt = f.nnz_in[j] * (1 if (self.reduce_in and self.reduce_in[j]) else N)
+            if a.size != cnt:
+                raise CcuError("input %d: expected %d values, got %d" % (j, cnt, a.size))
+            ins.append(a)
+        outs = []
+        for j in range(f.n_out):
+            if want is not None and not want[j]:
+                outs.append(None)
+            else:
+                cnt = f.nnz_out[j] * (1 if (self.reduce_out and self.reduce_out[j]) else N)
+                outs.append(np.full(cnt, np.nan))
+        a = capi.ptr_array([None if x is None or x.size == 0 else x.ctypes.data for x in ins])
+        r = capi.ptr_array([None if x is None or x.size == 0 else x.ctypes.data for x in outs])
+        L = capi.lib()
+        if self.reduce_in is None and self.reduce_out is None:
+            capi.check(L.ccu_map_eval_host(f.handle, N, a, r))
+        else:
+            ri, ro = capi.int_array(self.reduce_in), capi.int_array(self.reduce_out)
+            capi.check(L.ccu_map_eval_reduce_host(
+                f.handle, N, a, r, None if ri is None else ri.ctypes.data_as(capi.c_i_p),
+                None if ro is None else ro.ctypes.data_as(capi.c_i_p)))
+        return outs

@@ -1,0 +1,149 @@
+/*
+ * casadi_cuda.h -- C ABI of libcasadi_cuda.so, the B200 (sm_100a) evaluator behind
+ * CasADi's `Function::map(N, "cuda")`.
+ *
+ * Plain C: pointers and sizes only, no CasADi, torch or CUDA types in any signature
+ * (a CUDA stream is passed as void*).  Each entry point names the reference interface
+ * it replaces (paths relative to the casadi/casadi 3.7.2 tree).  `casadi_b200/host/cuda_map.cpp`
+ * (the `CudaMap` subclass of casadi::Map) and `casadi_b200/capi.py` (ctypes) are the two
+ * bindings shipped in this repository; INTEGRATION.md shows the reference-side patch.
+ *
+ * Conventions
+ *   - every function returning int returns 0 on success, non-zero on failure; the message is
+ *     available from ccu_last_error() (thread-local).  There is NO CPU fallback: when no CUDA
+ *     device is usable the create/eval calls fail.
+ *   - ccu_int is casadi_int (long long, casadi/core/casadi_types.hpp:29-38).
+ *   - "AoS" is the reference's Map layout: instance i of input j is arg[j][i*nnz_in[j] .. +nnz_in[j])
+ *     (casadi/core/map.cpp:149-154, map.hpp:77-82).  "SoA" is [k][i]: element k of instance i at
+ *     arg[j][k*N + i] (device-resident fast path, fully coalesced).
+ */
+#ifndef CASADI_CUDA_H
+#define CASADI_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define CCU_EXPORT __declspec(dllexport)
+#else
+#define CCU_EXPORT __attribute__((visibility("default")))
+#endif
+
+typedef long long ccu_int;
+
+#define CCU_ABI_VERSION 1
+#define CCU_LAYOUT_AOS 0
+#define CCU_LAYOUT_SOA 1
+
+/* opaque handles */
+typedef struct ccu_tape ccu_tape;     /* a compiled SX instruction tape, resident on one device      */
+typedef struct ccu_linsol ccu_linsol; /* a symbolic LDL / QR factorisation shared by a whole batch   */
+typedef struct ccu_comm ccu_comm;     /* a set of NCCL communicators (reduce_out sums across GPUs)   */
+
+/* ------------------------------------------------------------------------------------------------
+ * library
+ * ---------------------------------------------------------------------------------------------- */
+CCU_EXPORT int ccu_abi_version(void);
+CCU_EXPORT const char* ccu_last_error(void);
+/* number of usable CUDA devices (0 when there is none; never an error) */
+CCU_EXPORT int ccu_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * SX tape  --  replaces SXFunction::eval (casadi/core/sx_function.cpp:72-127) over the tape
+ * `std::vector<ScalarAtomic> algorithm_` (sx_function.hpp:37-44,258), exported through the public
+ * accessors Function::n_instructions/instruction_id/_input/_output/_constant (function.hpp:1114-1138).
+ *
+ * op[k]  : enum Operation value (calculus.hpp:60-218)
+ * i0[k]  : destination work slot            (OP_OUTPUT: output index)
+ * i1,i2  : source work slots                (OP_INPUT: input index, nonzero index;
+ *                                            OP_OUTPUT: i1 = source slot, i2 = nonzero index)
+ * d[k]   : value of an OP_CONST instruction
+ * sz_w   : work vector length (SXFunction::worksize_)
+ * Fails (NULL) for tapes the device cannot evaluate: OP_CALL, OP_PARAMETER (free variables,
+ * sx_function.cpp:78-83), OP_PRINTME, unknown opcodes, out-of-range indices.
+ * ---------------------------------------------------------------------------------------------- */
+CCU_EXPORT ccu_tape* ccu_tape_create(ccu_int n_instr, const int* op, const int* i0, const int* i1,
+                                     const int* i2, const double* d, ccu_int sz_w, ccu_int n_in,
+                                     const ccu_int* nnz_in, ccu_int n_out, const ccu_int* nnz_out,
+                                     int device);
+CCU_EXPORT void ccu_tape_destroy(ccu_tape* t);
+
+/* static facts about a compiled tape (all per ONE evaluation) */
+typedef struct ccu_tape_info {
+  ccu_int n_instr;        /* instructions in the source tape                                         */
+  ccu_int n_words;        /* 8-byte words of the packed device program                               */
+  ccu_int flops;          /* arithmetic tape instructions (op<OP_CONST minus ASSIGN, +5)  */
+  ccu_int bytes_in;       /* 8 * sum nnz_in                                                          */
+  ccu_int bytes_out;      /* 8 * sum nnz_out                                                         */
+  ccu_int sz_w;           /* work slots of the source tape                                           */
+  ccu_int slots_shared;   /* work slots kept in shared memory per instance                           */
+  ccu_int slots_global;   /* work slots spilled to the global scratch per instance                   */
+  ccu_int threads;        /* CTA size the plan launches                                              */
+  ccu_int ipt;            /* instances per thread                                                    */
+  ccu_int smem_bytes;     /* dynamic shared memory per CTA                                           */
+  ccu_int spill_loads;    /* global-scratch reads per evaluation                                     */
+  ccu_int spill_stores;   /* global-scratch writes per evaluation                                    */
+  ccu_int reserved[3];
+} ccu_tape_info;
+CCU_EXPORT int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info);
+
+/* Debug/verification access to the packed device program (ISA: casadi_b200/csrc/ccu_isa.h):
+ * copies min(cap, n_words) words and returns n_words.  `device` = -1 in ccu_tape_create compiles
+ * without a GPU (such a tape can be inspected but never evaluated). */
+CCU_EXPORT ccu_int ccu_tape_get_program(const ccu_tape* t, unsigned long long* words, ccu_int cap);
+
+/* Tunables of the plan (threads per CTA, instances per thread, shared slots); 0 = choose
+ * automatically.  Replaces nothing in the reference: Map::create passes an empty Dict (map.cpp:43-47). */
+CCU_EXPORT int ccu_tape_set_plan(ccu_tape* t, int threads, int ipt, int slots_shared);
+
+/* ------------------------------------------------------------------------------------------------
+ * Map evaluation  --  replaces Map::eval / Map::eval_gen (casadi/core/map.cpp:141-157, 327-334) and
+ * OmpMap::eval (map.cpp:340-386).
+ *
+ * ccu_map_eval_host: arg[j], res[j] are HOST pointers in the reference's AoS layout; arg[j]==NULL
+ * reads as zeros (sx_function.cpp:116), res[j]==NULL is not computed (:117).  Does H2D, the kernel
+ * and D2H; returns after the results are in res.
+ * ---------------------------------------------------------------------------------------------- */
+CCU_EXPORT int ccu_map_eval_host(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res);
+
+/* Same with DEVICE pointers (on the tape's device) and an explicit layout; asynchronous on `stream`
+ * (a cudaStream_t, NULL = the legacy default stream).  This is the call the roofline is measured on. */
+CCU_EXPORT int ccu_map_eval_device(ccu_tape* t, ccu_int N, const double* const* d_arg,
+                                   double* const* d_res, int layout, void* stream);
+
+/* Map with reductions -- replaces HorzRepmat/HorzRepsum around a Map (function.cpp:797-818,
+ * repmat.cpp:44-50,127-135) and MapSum::eval_gen (mapsum.cpp:154-186).
+ * reduce_in[j]!=0 : input j is ONE instance (nnz_in[j] doubles) broadcast to all N evaluations.
+ * reduce_out[j]!=0: output j is the sum over the N evaluations (nnz_out[j] doubles).
+ * The device sum is a fixed-shape pairwise tree (independent of launch geometry and GPU count);
+ * it differs from the reference's sequential sum by rounding only. Pointers as in ccu_map_eval_host. */
+CCU_EXPORT int ccu_map_eval_reduce_host(ccu_tape* t, ccu_int N, const double* const* arg,
+                                        double* const* res, const int* reduce_in, const int* reduce_out);
+CCU_EXPORT int ccu_map_eval_reduce_device(ccu_tape* t, ccu_int N, const double* const* d_arg,
+                                          double* const* d_res, const int* reduce_in,
+                                          const int* reduce_out, int layout, void* stream);
+
+/* Time (ms) of the most recent kernel launch sequence of this tape, measured with CUDA events on
+ * the launching stream (synchronises).  FStats analogue (casadi/core/timing.hpp:47-98). */
+CCU_EXPORT int ccu_tape_last_kernel_ms(ccu_tape* t, double* ms);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+CCU_EXPORT ccu_int ccu_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device memory helpers (so a C or C++ host needs no CUDA headers)
+ * ---------------------------------------------------------------------------------------------- */
+CCU_EXPORT int ccu_set_device(int device);
+CCU_EXPORT void* ccu_malloc(ccu_int bytes);
+CCU_EXPORT int ccu_free(void* p);
+CCU_EXPORT void* ccu_malloc_host(ccu_int bytes); /* pinned */
+CCU_EXPORT int ccu_free_host(void* p);
+CCU_EXPORT int ccu_memcpy_h2d(void* dst, const void* src, ccu_int bytes, void* stream);
+CCU_EXPORT int ccu_memcpy_d2h(void* dst, const void* src, ccu_int bytes, void* stream);
+CCU_EXPORT int ccu_stream_sync(void* stream);
+CCU_EXPORT int ccu_device_sync(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CASADI_CUDA_H */

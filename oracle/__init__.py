@@ -129,3 +129,14 @@ def mtimes(x, sp_x, y, sp_y, z, sp_z):
     L.oracle_mtimes(_p(x, c_d_p), _p(sp_x, c_ll_p), _p(y, c_d_p), _p(sp_y, c_ll_p), _p(z, c_d_p),
                     _p(sp_z, c_ll_p), _p(w, c_d_p))
     return z
+
+
+def vec_op(op, x, y):
+    """Elementwise reference scalar op (opcode numbering of calculus.hpp) on float64 arrays."""
+    L = lib()
+    x = np.ascontiguousarray(x, np.float64); y = np.ascontiguousarray(y, np.float64)
+    f = np.empty_like(x)
+    rc = L.oracle_vec_op(ctypes.c_int(op), ctypes.c_longlong(x.size), _p(x, c_d_p), _p(y, c_d_p), _p(f, c_d_p))
+    if rc:
+        raise RuntimeError("oracle_vec_op: opcode %d not evaluable" % op)
+    return f

@@ -1,0 +1,205 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI
+(ccu_map_eval_host / ccu_map_eval_device), against the reference goldens and the pinned oracle.
+
+Bar (BASELINE.json north_star): bit-exact for +,-,*,/,sqrt, comparisons, if_else and the other exact
+operations; within 2 ulp for transcendentals -- the tolerance is ULP_TOL below.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from casadi_b200 import CudaMap, CudaTape, LAYOUT_AOS, LAYOUT_SOA, load_case, load_tape
+from util import EXACT_OPS, ULP_OPS, assert_bit_equal, exactify, tree_sum, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+ULP_TOL = 2          # transcendentals: |device - reference libm| <= 2 ulp
+COMPOSITE_RTOL = 1e-11  # whole tapes that chain transcendentals into arithmetic (ulp errors propagate)
+
+
+def opcover_output_ops():
+    """opcode that produced each output nonzero of the opcover function (single-op outputs only)."""
+    t = load_tape("opcover")
+    n = len(t["op"])
+    producer = {}
+    out_op = {}
+    depth = {}
+    for k in range(n):
+        op = int(t["op"][k])
+        if op in (44, 45):
+            producer[int(t["i0"][k])] = (op, 0)
+        elif op == 46:
+            out_op[int(t["i2"][k])] = producer[int(t["i1"][k])]
+        else:
+            d1 = producer[int(t["i1"][k])][1]
+            d2 = producer[int(t["i2"][k])][1]
+            producer[int(t["i0"][k])] = (op, max(d1, d2) + (0 if op in EXACT_OPS else 1))
+    return out_op
+
+
+@pytest.mark.parametrize("case_name", ["opcover", "opcover_special"])
+def test_operator_set_per_op(case_name):
+    tape = load_tape("opcover")
+    case = load_case(case_name)
+    N = case["N"]
+    got = CudaMap(tape, N)(case["in"])[0].reshape(N, -1)
+    want = case["out"][0].reshape(N, -1)
+    out_op = opcover_output_ops()
+    worst = {}
+    for j in range(want.shape[1]):
+        op, ntrans = out_op[j]
+        if ntrans == 0:
+            assert_bit_equal(got[:, j], want[:, j], "%s output %d (op %d, exact class)" % (case_name, j, op))
+        else:
+            u = ulp_diff(got[:, j], want[:, j])
+            worst[j] = (op, float(u.max()))
+            # chained transcendentals (e.g. log(fabs(a)+0.1)) still only contain ONE transcendental here
+            assert u.max() <= ULP_TOL * ntrans, "%s output %d (op %d): %g ulp at a=%r b=%r c=%r (got %r want %r)" % (
+                case_name, j, op, u.max(), case["in"][0][int(u.argmax())], case["in"][1][int(u.argmax())],
+                case["in"][2][int(u.argmax())], got[int(u.argmax()), j], want[int(u.argmax()), j])
+    print("worst ulp per transcendental output:", worst)
+
+
+@pytest.mark.parametrize("name", ["rocket_hess"])
+def test_exact_class_tapes_bit_exact_vs_reference(name):
+    tape, case = load_tape(name), load_case(name)
+    ops = set(int(o) for o in tape["op"]) - {44, 45, 46}
+    assert ops <= EXACT_OPS, ops - EXACT_OPS
+    outs = CudaMap(tape, case["N"])(case["in"])
+    for j, (g, w) in enumerate(zip(outs, case["out"])):
+        assert_bit_equal(g, w, "%s out%d" % (name, j))
+
+
+@pytest.mark.parametrize("name", ["cartpole", "cartpole1", "quad1", "quad", "quad_fwd", "quad_adj", "quad_jac",
+                                  "quad1_jac", "mc", "mcstep", "mapnode"])
+def test_exactified_tapes_bit_exact_vs_oracle(name):
+    tape, case = exactify(load_tape(name)), load_case(name)
+    N = min(case["N"], 200)
+    ins = [a[:N * int(n)] for a, n in zip(case["in"], tape["nnz_in"])]
+    want = oracle.map_eval(tape, N, ins)
+    got = CudaMap(tape, N)(ins)
+    for j, (g, w) in enumerate(zip(got, want)):
+        assert_bit_equal(g, w, "%s(exactified) out%d" % (name, j))
+
+
+@pytest.mark.parametrize("name", ["cartpole", "cartpole1", "quad1", "quad", "quad_fwd", "quad_adj", "quad_jac",
+                                  "quad1_jac", "mc", "mcstep", "mapnode"])
+def test_composite_tapes_vs_reference(name):
+    tape, case = load_tape(name), load_case(name)
+    outs = CudaMap(tape, case["N"])(case["in"])
+    for j, (g, w) in enumerate(zip(outs, case["out"])):
+        scale = np.maximum(np.abs(w), 1.0)
+        err = np.abs(g - w) / scale
+        assert np.all(np.isfinite(g) == np.isfinite(w))
+        assert np.nanmax(err, initial=0.0) <= COMPOSITE_RTOL, "%s out%d: rel err %g" % (name, j, np.nanmax(err))
+
+
+@pytest.mark.parametrize("name,plans", [("cartpole", [(128, 1, 0), (64, 2, 0), (256, 4, 0), (128, 1, 8), (32, 2, 5)]),
+                                        ("quad", [(128, 1, 48), (128, 2, 16), (64, 1, 128), (256, 1, 24)]),
+                                        ("quad1_jac", [(128, 1, 0), (128, 4, 12), (96, 2, 33)])])
+def test_every_plan_gives_identical_bits(name, plans):
+    """threads / instances-per-thread / shared-slot budget change where values live, never what is computed."""
+    tape, case = load_tape(name), load_case(name)
+    t = CudaTape(tape)
+    ref = None
+    for (threads, ipt, S) in plans:
+        t.set_plan(threads, ipt, S)
+        outs = CudaMap(t, case["N"])(case["in"])
+        if ref is None:
+            ref = outs
+        else:
+            for j, (g, w) in enumerate(zip(outs, ref)):
+                assert_bit_equal(g, w, "%s plan %r out%d" % (name, (threads, ipt, S), j))
+
+
+@pytest.mark.parametrize("N", [1, 2, 31, 32, 33, 127, 128, 129, 255, 257, 1000])
+def test_ragged_batch_sizes(N):
+    tape, case = load_tape("cartpole1"), load_case("cartpole1")
+    N = min(N, case["N"])
+    ins = [a[:N * int(n)] for a, n in zip(case["in"], tape["nnz_in"])]
+    full = CudaMap(tape, case["N"])(case["in"])
+    got = CudaMap(tape, N)(ins)
+    for j in range(len(got)):
+        assert_bit_equal(got[j], full[j][:N * int(tape["nnz_out"][j])], "N=%d out%d" % (N, j))
+
+
+def test_null_argument_reads_zero_null_result_skipped():
+    # reference semantics: sx_function.cpp:116-117
+    tape, case = load_tape("mapnode"), load_case("mapnode")
+    N = case["N"]
+    ins = list(case["in"])
+    m = CudaMap(tape, N)
+    zero = m([ins[0], np.zeros_like(ins[1]), ins[2], ins[3]])
+    part = m([ins[0], None, ins[2], ins[3]], want=[True, False, True])
+    assert part[1] is None
+    assert_bit_equal(part[0], zero[0])
+    assert_bit_equal(part[2], zero[2])
+    want = oracle.map_eval(tape, N, [ins[0], None, ins[2], ins[3]], want=[True, False, True])
+    assert np.allclose(part[0], want[0], rtol=1e-13, atol=0)
+
+
+def test_device_pointer_api_soa_and_aos_layouts():
+    import torch
+    tape, case = load_tape("quad1"), load_case("quad1")
+    N = case["N"]
+    t = CudaTape(tape)
+    host = CudaMap(t, N)(case["in"])
+    dev = torch.device("cuda:0")
+    for layout in (LAYOUT_AOS, LAYOUT_SOA):
+        d_in, d_out = [], []
+        for a, n in zip(case["in"], t.nnz_in):
+            x = torch.from_numpy(a.reshape(N, n).copy())
+            x = x if layout == LAYOUT_AOS else x.t().contiguous()
+            d_in.append(x.to(dev))
+        for n in t.nnz_out:
+            d_out.append(torch.full((N, n) if layout == LAYOUT_AOS else (n, N), float("nan"), dtype=torch.float64, device=dev))
+        torch.cuda.synchronize()
+        t.eval_device(N, [x.data_ptr() for x in d_in], [x.data_ptr() for x in d_out], layout=layout,
+                      stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        for j, y in enumerate(d_out):
+            y = y if layout == LAYOUT_AOS else y.t().contiguous()
+            assert_bit_equal(y.cpu().numpy().ravel(), host[j], "layout %d out%d" % (layout, j))
+        assert t.last_kernel_ms() > 0
+
+
+def test_reduce_out_fixed_tree_and_reference_sum():
+    tape, case, ref = load_tape("mc"), load_case("mc"), load_case("mc_sum")
+    N = case["N"]
+    per = CudaMap(tape, N)(case["in"])
+    red = CudaMap(tape, N, reduce_in=[0, 0], reduce_out=[1, 1])(case["in"])
+    for j, nnz in enumerate((4, 1)):
+        # (1) bit-exact against the documented summation tree applied to the per-instance device results
+        assert_bit_equal(red[j], tree_sum(per[j].reshape(N, nnz)), "tree out%d" % j)
+        # (2) against the reference's sequential HorzRepsum within the summation-order bound N*eps*sum|x|
+        bound = N * np.finfo(float).eps * np.abs(case["out"][j].reshape(N, nnz)).sum(axis=0) + 1e-11 * np.abs(ref["out"][j])
+        assert np.all(np.abs(red[j] - ref["out"][j]) <= bound), (red[j], ref["out"][j])
+
+
+def test_reduce_in_broadcast():
+    tape, case = load_tape("quad1"), load_case("quad1")
+    N = 300
+    u0 = case["in"][1][:4].copy()
+    x = np.tile(case["in"][0][:12 * 100], 3)
+    full = CudaMap(tape, N)([x, np.tile(u0, N)])
+    bc = CudaMap(tape, N, reduce_in=[0, 1], reduce_out=[0])([x, u0])
+    assert_bit_equal(bc[0], full[0])
+
+
+def test_large_batch_periodic_inputs_full_size():
+    """BASELINE size (N=1e6): inputs repeat with period P, so outputs must repeat bit-for-bit and the first
+    period must match the reference golden -- a size-independent property."""
+    tape, case = load_tape("cartpole"), load_case("cartpole")
+    P, N = case["N"], 1_000_000
+    reps = N // P
+    ins = [np.tile(a, reps) for a in case["in"]]
+    out = CudaMap(tape, P * reps)(ins)[0].reshape(reps, -1)
+    assert (out.view(np.uint64) == out[0].view(np.uint64)).all()
+    err = np.abs(out[0] - case["out"][0]) / np.maximum(np.abs(case["out"][0]), 1.0)
+    assert err.max() <= COMPOSITE_RTOL
+
+
+def test_zero_batch_is_rejected_like_the_reference():
+    from casadi_b200 import CcuError
+    with pytest.raises(CcuError):
+        CudaMap(load_tape("cartpole1"), 0)

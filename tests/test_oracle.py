@@ -8,22 +8,12 @@ import pytest
 
 import oracle
 from casadi_b200.tapeio import load_case, load_tape
+from util import assert_bit_equal
 
 SX_CASES = [("cartpole", "cartpole"), ("cartpole1", "cartpole1"), ("quad", "quad"), ("quad1", "quad1"),
             ("quad_fwd", "quad_fwd"), ("quad_adj", "quad_adj"), ("quad_jac", "quad_jac"),
             ("quad1_jac", "quad1_jac"), ("rocket_hess", "rocket_hess"), ("mcstep", "mcstep"), ("mc", "mc"),
             ("mapnode", "mapnode"), ("opcover", "opcover"), ("opcover", "opcover_special")]
-
-
-def bits(a):
-    return np.ascontiguousarray(a, np.float64).view(np.uint64)
-
-
-def assert_bit_equal(got, want, what=""):
-    g, w = bits(got), bits(want)
-    same = (g == w) | (np.isnan(got) & np.isnan(want))
-    assert same.all(), "%s: %d/%d values differ (first at %d: %r vs %r)" % (
-        what, (~same).sum(), same.size, np.argmax(~same), got[np.argmax(~same)], want[np.argmax(~same)])
 
 
 @pytest.mark.parametrize("tape_name,case_name", SX_CASES)
