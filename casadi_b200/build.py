@@ -9,7 +9,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libcasadi_cuda.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CU_SOURCES = ["interp.cu", "reduce.cu", "capi.cu"]
+CU_SOURCES = ["interp.cu", "reduce.cu", "capi.cu", "diag.cu"]
 CPP_SOURCES = ["tape_compile.cpp"]
 # -fmad=false: no FMA contraction, the rounding contract of the whole library (see ccu_ops.cuh)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",

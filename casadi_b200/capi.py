@@ -37,6 +37,7 @@ SYMBOLS = {
     "ccu_map_eval_reduce_device": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_i_p, c_i_p, ctypes.c_int, c_vp]),
     "ccu_tape_last_kernel_ms": (ctypes.c_int, [c_vp, c_d_p]),
     "ccu_launch_count": (c_ll, []),
+    "ccu_fp64_issue_rate": (ctypes.c_int, [ctypes.c_int, c_d_p]),
     "ccu_set_device": (ctypes.c_int, [ctypes.c_int]),
     "ccu_malloc": (c_vp, [c_ll]),
     "ccu_free": (ctypes.c_int, [c_vp]),

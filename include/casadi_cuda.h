@@ -129,6 +129,9 @@ CCU_EXPORT int ccu_map_eval_reduce_device(ccu_tape* t, ccu_int N, const double* 
 CCU_EXPORT int ccu_tape_last_kernel_ms(ccu_tape* t, double* ms);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 CCU_EXPORT ccu_int ccu_launch_count(void);
+/* Measured FP64 non-FMA issue rate (DADD/s) of `device`: the FP64 denominator of the roofline (SURVEY 8d;
+ * contraction is off by contract, so one tape instruction is at best one DADD).  Runs a ~3 ms microbenchmark. */
+CCU_EXPORT int ccu_fp64_issue_rate(int device, double* ops_per_s);
 
 /* ------------------------------------------------------------------------------------------------
  * Device memory helpers (so a C or C++ host needs no CUDA headers)

@@ -36,7 +36,10 @@ def ulp_diff(got, want):
     a = got[fin].view(np.int64).copy(); b = want[fin].view(np.int64).copy()
     # map the sign-magnitude bit patterns to a monotone integer line
     a = np.where(a < 0, np.int64(-2**63) - a, a); b = np.where(b < 0, np.int64(-2**63) - b, b)
-    out[fin] = np.abs(a.astype(np.float64) - b.astype(np.float64))
+    # subtract as integers (float64 cannot resolve neighbouring int64 near 2**62); a huge distance between
+    # values of opposite sign may wrap, which is harmless here (it stays huge) after the float conversion below
+    d = a - b
+    out[fin] = np.where(d == np.int64(-2**63), 2.0**63, np.abs(d).astype(np.float64))
     out[~fin & ~same] = np.inf
     return out
 
