@@ -64,7 +64,7 @@ def run_ref_bench(n, reps, warm, threads):
     out = subprocess.run([exe, "quad_ms", str(n), "openmp", str(threads), str(reps), str(warm)], env=env,
                          capture_output=True, text=True, timeout=1500)
     if out.returncode != 0:
-        raise RuntimeError("ref_bench failed: " + out.stderr[-500:])
+        raise RuntimeError("ref_bench rc=%d: %s" % (out.returncode, (out.stderr or out.stdout)[-300:]))
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 

@@ -19,6 +19,10 @@ c_vp = ctypes.c_void_p
 
 LAYOUT_AOS = 0
 LAYOUT_SOA = 1
+MODE_INTERP = 0
+MODE_JIT = 1
+MODE_AUTO = 2
+MODES = {"interp": MODE_INTERP, "jit": MODE_JIT, "auto": MODE_AUTO, None: -1}
 
 # every symbol include/casadi_cuda.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -31,6 +35,10 @@ SYMBOLS = {
     "ccu_tape_get_info": (ctypes.c_int, [c_vp, c_vp]),
     "ccu_tape_get_program": (c_ll, [c_vp, c_vp, c_ll]),
     "ccu_tape_set_plan": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "ccu_tape_set_mode": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "ccu_set_default_mode": (ctypes.c_int, [ctypes.c_int]),
+    "ccu_tape_set_jit_plan": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_ll]),
+    "ccu_tape_get_jit_source": (c_ll, [c_vp, c_ll, c_vp, c_ll]),
     "ccu_map_eval_host": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp]),
     "ccu_map_eval_device": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, ctypes.c_int, c_vp]),
     "ccu_map_eval_reduce_host": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_i_p, c_i_p]),
@@ -53,7 +61,9 @@ SYMBOLS = {
 class TapeInfo(ctypes.Structure):
     _fields_ = [(n, c_ll) for n in ("n_instr", "n_words", "flops", "bytes_in", "bytes_out", "sz_w", "slots_shared",
                                     "slots_global", "threads", "ipt", "smem_bytes", "spill_loads", "spill_stores",
-                                    "max_live", "grid", "ctas_per_sm")]
+                                    "max_live", "grid", "ctas_per_sm", "mode", "jit_segments",
+                                    "jit_scratch_slots", "jit_tile", "jit_compile_ms", "jit_cross_loads",
+                                    "jit_cross_stores", "jit_max_regs", "jit_cache_hits", "jit_threads")]
 
 
 _lib = None

@@ -15,6 +15,7 @@
 
 #include "ccu_isa.h"
 #include "interp.cuh"
+#include "jit.hpp"
 #include "reduce.cuh"
 #include "tape_compile.hpp"
 
@@ -22,6 +23,7 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_default_mode{-1};  // -1: from the environment variable CCU_MODE
 
 int fail(const char* fmt, ...) {
   char buf[1024];
@@ -82,6 +84,13 @@ struct ccu_tape {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
+  // specialised kernels (jit.hpp); mode: CCU_MODE_INTERP or CCU_MODE_JIT
+  int mode = CCU_MODE_INTERP;
+  ccu::JitOptions jit_opt;
+  ccu::JitProgram jit;
+  bool jit_built = false;
+  std::string jit_error;
+  int sms = 0;
 
   ccu::TapeSource source() const {
     ccu::TapeSource s;
@@ -142,6 +151,18 @@ int ensure_scratch(ccu_tape* t) {
 }
 
 int launch(ccu_tape* t, const ccu::IoDesc& io, long long N, cudaStream_t stream) {
+  if (t->mode == CCU_MODE_JIT) {
+    const long long tile = ccu::jit_tile_for(t->jit, N, t->sms);
+    if (t->jit.scratch_slots > 0 && t->scratch.ensure(static_cast<size_t>(t->jit.scratch_slots) * tile)) return 1;
+    if (t->ev0) cudaEventRecord(t->ev0, stream);
+    long long nl = 0;
+    cudaError_t e = ccu::jit_launch(t->jit, io, N, t->scratch.p, tile, stream, &nl);
+    g_launches += nl;
+    if (e != cudaSuccess) return fail("specialised kernel launch failed: %s", cudaGetErrorString(e));
+    if (t->ev1) cudaEventRecord(t->ev1, stream);
+    t->timed = true;
+    return 0;
+  }
   if (ensure_scratch(t)) return 1;
   if (t->ev0) cudaEventRecord(t->ev0, stream);
   cudaError_t e = ccu::launch_interp(t->plan, t->d_prog, io, N, t->scratch.p, stream);
@@ -149,6 +170,33 @@ int launch(ccu_tape* t, const ccu::IoDesc& io, long long N, cudaStream_t stream)
   if (t->ev1) cudaEventRecord(t->ev1, stream);
   t->timed = true;
   if (N > 0) g_launches++;
+  return 0;
+}
+
+void jit_options_from_env(ccu::JitOptions* o) {
+  if (const char* p = getenv("CCU_JIT_SEG")) o->seg_instr = atoi(p);
+  if (const char* p = getenv("CCU_JIT_THREADS")) o->threads = atoi(p);
+  if (const char* p = getenv("CCU_JIT_MINBLOCKS")) o->min_blocks = atoi(p);
+  if (const char* p = getenv("CCU_JIT_BATCH")) o->load_batch = atoi(p);
+  if (const char* p = getenv("CCU_JIT_TILE")) o->tile = atoll(p);
+}
+
+// (re)build the specialised kernels with the tape's current jit options
+int build_jit(ccu_tape* t) {
+  if (t->device < 0) return fail("tape was compiled without a CUDA device");
+  if (t->jit_opt.threads % 32 != 0 || t->jit_opt.threads < 32 || t->jit_opt.threads > 1024)
+    return fail("jit: threads must be a multiple of 32 in [32, 1024]");
+  CCU_CUDA(cudaSetDevice(t->device));
+  ccu::JitProgram prog;
+  std::string err;
+  if (!ccu::jit_build(t->source(), t->jit_opt, t->device, &prog, &err)) {
+    t->jit_error = err;
+    return fail("tape specialisation failed: %s", err.c_str());
+  }
+  if (t->jit_built) ccu::jit_destroy(&t->jit);
+  t->jit = std::move(prog);
+  t->jit_built = true;
+  t->jit_error.clear();
   return 0;
 }
 
@@ -234,6 +282,31 @@ ccu_tape* ccu_tape_create(ccu_int n_instr, const int* op, const int* i0, const i
     return nullptr;
   }
   t->d_in.resize(n_in); t->d_out.resize(n_out); t->d_part.resize(n_out);
+  // execution mode: CCU_MODE = interp | jit | auto (default).  "auto" specialises the tape when NVRTC is
+  // loadable and the compilation succeeds, and otherwise runs the interpreter kernel.
+  jit_options_from_env(&t->jit_opt);
+  if (t->device >= 0) {
+    cudaDeviceGetAttribute(&t->sms, cudaDevAttrMultiProcessorCount, t->device);
+    const char* m = getenv("CCU_MODE");
+    std::string want = m ? m : "auto";
+    const int dm = g_default_mode.load();
+    if (dm == CCU_MODE_INTERP) want = "interp";
+    else if (dm == CCU_MODE_JIT) want = "jit";
+    else if (dm == CCU_MODE_AUTO) want = "auto";
+    if (want != "interp" && want != "jit" && want != "auto") {
+      fail("CCU_MODE must be interp, jit or auto (got '%s')", want.c_str());
+      ccu_tape_destroy(t);
+      return nullptr;
+    }
+    if (want != "interp") {
+      if (build_jit(t) == 0) {
+        t->mode = CCU_MODE_JIT;
+      } else if (want == "jit") {
+        ccu_tape_destroy(t);
+        return nullptr;
+      }
+    }
+  }
   return t;
 }
 
@@ -242,6 +315,7 @@ void ccu_tape_destroy(ccu_tape* t) {
   if (t->device >= 0) {
     cudaSetDevice(t->device);
     if (t->d_prog) cudaFree(t->d_prog);
+    if (t->jit_built) ccu::jit_destroy(&t->jit);
     t->scratch.release(); t->d_tmp.release();
     for (auto& b : t->d_in) b.release();
     for (auto& b : t->d_out) b.release();
@@ -269,10 +343,66 @@ int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info) {
   info->smem_bytes = static_cast<ccu_int>(t->plan.smem_bytes);
   info->spill_loads = t->prog.spill_loads;
   info->spill_stores = t->prog.spill_stores;
-  info->reserved[0] = t->max_live;
-  info->reserved[1] = t->plan.grid;
-  info->reserved[2] = t->plan.ctas_per_sm;
+  info->max_live = t->max_live;
+  info->grid = t->plan.grid;
+  info->ctas_per_sm = t->plan.ctas_per_sm;
+  info->mode = t->mode;
+  if (t->jit_built) {
+    info->jit_segments = static_cast<ccu_int>(t->jit.kernels.size());
+    info->jit_scratch_slots = t->jit.scratch_slots;
+    info->jit_tile = t->jit.tile;
+    info->jit_compile_ms = static_cast<ccu_int>(t->jit.compile_ms);
+    info->jit_cross_loads = t->jit.cross_loads;
+    info->jit_cross_stores = t->jit.cross_stores;
+    info->jit_max_regs = t->jit.max_regs;
+    info->jit_cache_hits = t->jit.cache_hits;
+    info->jit_threads = t->jit.threads;
+  }
   return 0;
+}
+
+int ccu_set_default_mode(int mode) {
+  if (mode < -1 || mode > CCU_MODE_AUTO) return fail("unknown mode %d", mode);
+  g_default_mode = mode;
+  return 0;
+}
+
+int ccu_tape_set_mode(ccu_tape* t, int mode) {
+  if (!t) return fail("null tape");
+  if (mode == CCU_MODE_INTERP) { t->mode = CCU_MODE_INTERP; return 0; }
+  if (mode != CCU_MODE_JIT) return fail("unknown mode %d", mode);
+  if (!t->jit_built && build_jit(t)) return 1;
+  t->mode = CCU_MODE_JIT;
+  return 0;
+}
+
+int ccu_tape_set_jit_plan(ccu_tape* t, int seg_instr, int threads, int min_blocks, ccu_int tile) {
+  if (!t) return fail("null tape");
+  ccu::JitOptions o = t->jit_opt;
+  if (seg_instr > 0) o.seg_instr = seg_instr;
+  if (threads > 0) o.threads = threads;
+  if (min_blocks >= 0) o.min_blocks = min_blocks;
+  if (tile >= 0) o.tile = tile;
+  std::swap(o, t->jit_opt);
+  if (build_jit(t)) { std::swap(o, t->jit_opt); return 1; }
+  t->mode = CCU_MODE_JIT;
+  return 0;
+}
+
+ccu_int ccu_tape_get_jit_source(const ccu_tape* t, ccu_int segment, char* buf, ccu_int cap) {
+  if (!t) { fail("null tape"); return -1; }
+  std::vector<std::string> src;
+  std::string err;
+  if (!ccu::jit_generate(t->source(), t->jit_opt, &src, nullptr, &err)) { fail("%s", err.c_str()); return -1; }
+  if (segment < 0) return static_cast<ccu_int>(src.size());
+  if (segment >= static_cast<ccu_int>(src.size())) { fail("segment out of range"); return -1; }
+  const std::string& s = src[segment];
+  if (buf && cap > 0) {
+    size_t n = std::min<size_t>(s.size(), static_cast<size_t>(cap) - 1);
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return static_cast<ccu_int>(s.size());
 }
 
 int ccu_tape_set_plan(ccu_tape* t, int threads, int ipt, int slots_shared) {

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(1024) ccu_interp_kernel(const uint64_t* __rest
           case D_ERFINV: CCU_FOR_E_ROLLED r[e] = op_erfinv(x[e]); break;
           case D_LOG1P: CCU_FOR_E_ROLLED r[e] = log1p(x[e]); break;
           case D_EXPM1: CCU_FOR_E_ROLLED r[e] = expm1(x[e]); break;
-          default: CCU_FOR_E r[e] = CUDART_NAN; break;
+          default: CCU_FOR_E r[e] = CCU_NAN; break;
         }
         CCU_FOR_E acc[e] = r[e];
         if (fd != D_NONE) { double* p = my_w + (size_t)fd * WS; CCU_FOR_E p[e * BD] = r[e]; }
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(1024) ccu_interp_kernel(const uint64_t* __rest
           case D_REMAINDER: CCU_FOR_E_ROLLED r[e] = remainder(x[e], y[e]); break;
           case D_ATAN2: CCU_FOR_E_ROLLED r[e] = atan2(x[e], y[e]); break;
           case D_HYPOT: CCU_FOR_E_ROLLED r[e] = hypot(x[e], y[e]); break;
-          default: CCU_FOR_E r[e] = CUDART_NAN; break;
+          default: CCU_FOR_E r[e] = CCU_NAN; break;
         }
         CCU_FOR_E acc[e] = r[e];
         if (fd != D_NONE) { double* p = my_w + (size_t)fd * WS; CCU_FOR_E p[e * BD] = r[e]; }

@@ -1,0 +1,70 @@
+// Tape specialisation ("jit" mode): an SX tape is turned into straight-line sm_100a kernels whose work
+// vector lives in REGISTERS (static register indices are the one thing an interpreter cannot have --
+// SURVEY 7 "central risk" ii), compiled at tape-creation time by NVRTC with --fmad=false.
+//
+// This is the analogue of the reference's own `jit` option (FunctionInternal option "jit",
+// casadi/core/function_internal.cpp; code generator SXFunction::codegen_body, sx_function.cpp:344-434),
+// not a replacement of the interpreter: when NVRTC is not loadable, or a tape fails to compile, the tape
+// runs on the interpreter kernel (interp.cu).  Never a CPU path.
+//
+// Long tapes are cut into SEGMENTS of ~seg_instr arithmetic instructions, one kernel each, so that ptxas
+// sees bounded basic blocks (compile time is superlinear in block length) and segments compile in parallel.
+// Values that cross a segment boundary travel through a global scratch laid out [slot][instance of the
+// tile] (coalesced); constants and inputs are re-materialised.  The batch is processed in tiles so the
+// scratch is sized by the tile, not by N.  The ORDER of operations and every operand pairing is the tape's:
+// each value is computed by the same IEEE operation from the same operand values as in SXFunction::eval
+// (sx_function.cpp:111-124).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "interp.cuh"
+#include "tape_compile.hpp"
+
+namespace ccu {
+
+struct JitOptions {
+  int seg_instr = 1000;   // arithmetic instructions per segment
+  int threads = 128;      // CTA size
+  int min_blocks = 4;     // __launch_bounds__ second argument: 4 CTAs of 128 threads per SM = at most 128 registers (0 = up to 255)
+  int load_batch = 8;     // cross-segment live-ins are loaded in groups of this many (memory-level parallelism)
+  int compile_threads = 0;  // 0 = hardware concurrency (max 32)
+  long long tile = 0;     // instances per tile (0 = automatic)
+  std::string cache_dir;  // compiled cubins are cached here ("" = $CCU_JIT_CACHE or ~/.cache/casadi_cuda)
+};
+
+struct JitProgram {
+  std::vector<cudaLibrary_t> libs;
+  std::vector<cudaKernel_t> kernels;
+  int threads = 128;
+  int scratch_slots = 0;        // cross-segment values alive at once (per instance)
+  long long tile = 0;           // instances per tile (0 = whole batch in one tile)
+  long long cross_loads = 0;    // scratch reads per evaluation
+  long long cross_stores = 0;   // scratch writes per evaluation
+  int max_regs = 0;             // max registers per thread over the segments
+  int cache_hits = 0;
+  double compile_ms = 0;
+};
+
+// true when libnvrtc can be loaded in this process
+bool jit_available(std::string* why);
+
+// generate + compile + load.  `device` must be the current device.
+bool jit_build(const TapeSource& src, const JitOptions& opt, int device, JitProgram* out, std::string* err);
+
+// generated CUDA source of every segment (inspection / tests; no GPU or NVRTC needed)
+bool jit_generate(const TapeSource& src, const JitOptions& opt, std::vector<std::string>* sources,
+                  JitProgram* plan, std::string* err);
+
+// tile size actually used for a batch of N
+long long jit_tile_for(const JitProgram& p, long long N, int sms);
+
+// scratch must hold scratch_slots * jit_tile_for(N) doubles
+cudaError_t jit_launch(const JitProgram& p, const IoDesc& io, long long N, double* scratch, long long tile,
+                       cudaStream_t stream, long long* launches);
+
+void jit_destroy(JitProgram* p);
+
+}  // namespace ccu

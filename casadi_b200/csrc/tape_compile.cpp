@@ -86,15 +86,7 @@ bool map_op(int rop, int* dop, int* nop) {
   }
 }
 
-enum Kind : uint8_t { K_ARITH, K_CONST, K_INPUT, K_OUTPUT };
-
-struct Node {
-  uint8_t kind;
-  uint8_t dop;
-  int a = -1, b = -1;   // operand value ids (node indices); OUTPUT: a = source value
-  int idx = 0, nz = 0;  // INPUT: input index / nonzero; OUTPUT: output index / nonzero
-  double c = 0;         // CONST literal
-};
+}  // namespace
 
 bool build_graph(const TapeSource& s, std::vector<Node>* nodes, long long* flops, std::string* err) {
   const long long n = s.n_instr;
@@ -160,8 +152,6 @@ bool build_graph(const TapeSource& s, std::vector<Node>* nodes, long long* flops
   }
   return true;
 }
-
-}  // namespace
 
 bool analyse_tape(const TapeSource& src, long long* max_live, long long* flops, std::string* err) {
   std::vector<Node> nodes;

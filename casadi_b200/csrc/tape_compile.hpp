@@ -36,6 +36,19 @@ struct Program {
   long long smem_loads = 0, smem_stores = 0;  // shared-memory accesses of the emitted program
 };
 
+// The value graph (SSA) recovered from the slot stream: node k is tape instruction k; operands refer to the
+// defining node.  Shared by the interpreter's slot allocator and the specialising code generator (jit.cpp).
+enum Kind : uint8_t { K_ARITH, K_CONST, K_INPUT, K_OUTPUT };
+struct Node {
+  uint8_t kind;
+  uint8_t dop;          // DevOp (ccu_isa.h)
+  int a = -1, b = -1;   // operand value ids (node indices); OUTPUT: a = source value
+  int idx = 0, nz = 0;  // INPUT: input index / nonzero; OUTPUT: output index / nonzero
+  double c = 0;         // CONST literal
+};
+// Validates the tape and builds the graph; `flops` = arithmetic instructions.
+bool build_graph(const TapeSource& s, std::vector<Node>* nodes, long long* flops, std::string* err);
+
 // Validates the tape (throws nothing; returns false and sets err) and computes the number of
 // simultaneously live values -- what an allocation without spills needs.
 bool analyse_tape(const TapeSource& src, long long* max_live, long long* flops, std::string* err);

@@ -16,7 +16,8 @@ from .capi import CcuError, LAYOUT_AOS, LAYOUT_SOA  # noqa: F401
 class CudaTape:
     """A compiled SX tape resident on one device (ccu_tape)."""
 
-    def __init__(self, tape, device=0):
+    def __init__(self, tape, device=0, mode=None):
+        """mode: None (environment variable CCU_MODE, default auto), "interp", "jit" or "auto"."""
         L = capi.lib()
         self.nnz_in = [int(v) for v in tape["nnz_in"]]
         self.nnz_out = [int(v) for v in tape["nnz_out"]]
@@ -28,9 +29,13 @@ class CudaTape:
         nin = np.ascontiguousarray(self.nnz_in, np.int64)
         nout = np.ascontiguousarray(self.nnz_out, np.int64)
         p = lambda a, t: a.ctypes.data_as(t)  # noqa: E731
-        self.handle = L.ccu_tape_create(len(op), p(op, capi.c_i_p), p(i0, capi.c_i_p), p(i1, capi.c_i_p),
-                                        p(i2, capi.c_i_p), p(d, capi.c_d_p), int(tape["sz_w"]), len(nin),
-                                        p(nin, capi.c_ll_p), len(nout), p(nout, capi.c_ll_p), int(device))
+        capi.check(L.ccu_set_default_mode(capi.MODES[mode]))
+        try:
+            self.handle = L.ccu_tape_create(len(op), p(op, capi.c_i_p), p(i0, capi.c_i_p), p(i1, capi.c_i_p),
+                                            p(i2, capi.c_i_p), p(d, capi.c_d_p), int(tape["sz_w"]), len(nin),
+                                            p(nin, capi.c_ll_p), len(nout), p(nout, capi.c_ll_p), int(device))
+        finally:
+            L.ccu_set_default_mode(-1)
         if not self.handle:
             raise CcuError(capi.last_error())
         self.device = device
@@ -62,6 +67,26 @@ class CudaTape:
     def set_plan(self, threads=0, ipt=0, slots_shared=0):
         capi.check(capi.lib().ccu_tape_set_plan(self.handle, threads, ipt, slots_shared))
 
+    def set_mode(self, mode):
+        """capi.MODE_INTERP or capi.MODE_JIT (raises when the tape cannot be specialised)."""
+        capi.check(capi.lib().ccu_tape_set_mode(self.handle, mode))
+
+    def set_jit_plan(self, seg_instr=0, threads=0, min_blocks=-1, tile=-1):
+        capi.check(capi.lib().ccu_tape_set_jit_plan(self.handle, seg_instr, threads, min_blocks, tile))
+
+    def jit_sources(self):
+        L = capi.lib()
+        n = L.ccu_tape_get_jit_source(self.handle, -1, None, 0)
+        if n < 0:
+            raise CcuError(capi.last_error())
+        out = []
+        for k in range(n):
+            size = L.ccu_tape_get_jit_source(self.handle, k, None, 0)
+            buf = ctypes.create_string_buffer(size + 1)
+            L.ccu_tape_get_jit_source(self.handle, k, buf, size + 1)
+            out.append(buf.value.decode())
+        return out
+
     def program(self):
         L = capi.lib()
         n = L.ccu_tape_get_program(self.handle, None, 0)
@@ -92,10 +117,10 @@ class CudaMap:
     """f.map(N, "cuda"): evaluates the tape for N instances; host buffers in the reference's layout
     (instance i of input j = arg[j][i*nnz_in[j] : (i+1)*nnz_in[j]], casadi/core/map.cpp:149-154)."""
 
-    def __init__(self, tape, n, device=0, reduce_in=None, reduce_out=None):
+    def __init__(self, tape, n, device=0, reduce_in=None, reduce_out=None, mode=None):
         if n <= 0:
             raise CcuError("Degenerate map operation")  # function.cpp:862
-        self.f = tape if isinstance(tape, CudaTape) else CudaTape(tape, device)
+        self.f = tape if isinstance(tape, CudaTape) else CudaTape(tape, device, mode)
         self.n = int(n)
         self.reduce_in = list(reduce_in) if reduce_in is not None else None
         self.reduce_out = list(reduce_out) if reduce_out is not None else None

@@ -32,9 +32,12 @@ extern "C" {
 
 typedef long long ccu_int;
 
-#define CCU_ABI_VERSION 1
+#define CCU_ABI_VERSION 2
 #define CCU_LAYOUT_AOS 0
 #define CCU_LAYOUT_SOA 1
+#define CCU_MODE_INTERP 0 /* tape-interpreter kernel (always available)                                  */
+#define CCU_MODE_JIT 1    /* tape specialised into straight-line sm_100a kernels by NVRTC at create time */
+#define CCU_MODE_AUTO 2   /* JIT when possible, else INTERP (ccu_set_default_mode only)                  */
 
 /* opaque handles */
 typedef struct ccu_tape ccu_tape;     /* a compiled SX instruction tape, resident on one device      */
@@ -84,7 +87,19 @@ typedef struct ccu_tape_info {
   ccu_int smem_bytes;     /* dynamic shared memory per CTA                                           */
   ccu_int spill_loads;    /* global-scratch reads per evaluation                                     */
   ccu_int spill_stores;   /* global-scratch writes per evaluation                                    */
-  ccu_int reserved[3];
+  ccu_int max_live;       /* peak number of simultaneously live values of the tape                   */
+  ccu_int grid;           /* persistent grid of the interpreter plan                                 */
+  ccu_int ctas_per_sm;    /* resident CTAs per SM of the interpreter plan                            */
+  ccu_int mode;           /* CCU_MODE_INTERP / CCU_MODE_JIT: what the evaluation calls launch        */
+  ccu_int jit_segments;   /* specialised kernels per tile (0 = not built)                            */
+  ccu_int jit_scratch_slots; /* cross-segment values per instance                                    */
+  ccu_int jit_tile;       /* instances per tile (0 = automatic)                                      */
+  ccu_int jit_compile_ms; /* generation + NVRTC + load time                                          */
+  ccu_int jit_cross_loads;   /* scratch reads per evaluation                                         */
+  ccu_int jit_cross_stores;  /* scratch writes per evaluation                                        */
+  ccu_int jit_max_regs;   /* max registers per thread over the segments                              */
+  ccu_int jit_cache_hits; /* segments served from the cubin cache                                    */
+  ccu_int jit_threads;    /* CTA size of the specialised kernels                                     */
 } ccu_tape_info;
 CCU_EXPORT int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info);
 
@@ -92,6 +107,22 @@ CCU_EXPORT int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info);
  * copies min(cap, n_words) words and returns n_words.  `device` = -1 in ccu_tape_create compiles
  * without a GPU (such a tape can be inspected but never evaluated). */
 CCU_EXPORT ccu_int ccu_tape_get_program(const ccu_tape* t, unsigned long long* words, ccu_int cap);
+
+/* Execution mode.  ccu_tape_create honours the environment variable CCU_MODE = interp | jit | auto
+ * (default auto: specialise when NVRTC is loadable and the tape compiles, else interpret).  The reference's
+ * analogue is the Function option "jit" (casadi/core/function_internal.cpp, options "jit"/"compiler").
+ * ccu_tape_set_mode(CCU_MODE_JIT) fails when the specialisation is impossible; there is no CPU path. */
+CCU_EXPORT int ccu_tape_set_mode(ccu_tape* t, int mode);
+/* Process-wide default for subsequent ccu_tape_create calls: CCU_MODE_INTERP, CCU_MODE_JIT (create fails when
+ * the specialisation fails), CCU_MODE_AUTO, or -1 = take it from the environment (the initial state). */
+CCU_EXPORT int ccu_set_default_mode(int mode);
+/* Tunables of the specialisation: arithmetic instructions per segment, CTA size, __launch_bounds__
+ * min-blocks (0 = none), instances per tile (0 = automatic); arguments <= 0 (tile, min_blocks: < 0) keep the
+ * current value.  Rebuilds the kernels and selects CCU_MODE_JIT. */
+CCU_EXPORT int ccu_tape_set_jit_plan(ccu_tape* t, int seg_instr, int threads, int min_blocks, ccu_int tile);
+/* Generated CUDA source of segment `segment` (inspection/tests; works without a GPU): copies at most cap-1
+ * characters, returns the full length; segment < 0 returns the number of segments. */
+CCU_EXPORT ccu_int ccu_tape_get_jit_source(const ccu_tape* t, ccu_int segment, char* buf, ccu_int cap);
 
 /* Tunables of the plan (threads per CTA, instances per thread, shared slots); 0 = choose
  * automatically.  Replaces nothing in the reference: Map::create passes an empty Dict (map.cpp:43-47). */

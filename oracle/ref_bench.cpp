@@ -82,7 +82,9 @@ static Job make_job(const Function& f, long long n, const std::string& mode, int
 }
 
 static void run(Job& j) {
-  // eval() clobbers the pointer arrays' scratch tail only; the first n_in/n_out entries are preserved
+  // (re)bind the buffers: a Job may have been copied when the job list grew
+  for (size_t k = 0; k < j.in.size(); ++k) j.arg[k] = j.in[k].data();
+  for (size_t k = 0; k < j.out.size(); ++k) j.res[k] = j.out[k].data();
   int flag = j.F(j.arg.data(), j.res.data(), j.iw.data(), j.w.data(), 0);
   casadi_assert(flag == 0, "reference evaluation failed");
 }

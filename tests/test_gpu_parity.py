@@ -8,10 +8,11 @@ import numpy as np
 import pytest
 
 import oracle
-from casadi_b200 import CudaMap, CudaTape, LAYOUT_AOS, LAYOUT_SOA, load_case, load_tape
+from casadi_b200 import CudaMap, CudaTape, LAYOUT_AOS, LAYOUT_SOA, capi, load_case, load_tape
 from util import EXACT_OPS, ULP_OPS, assert_bit_equal, exactify, tree_sum, ulp_diff
 
 pytestmark = pytest.mark.gpu
+MODES = ["interp", "jit"]  # both product paths: the interpreter kernel and the NVRTC-specialised kernels
 
 ULP_TOL = 2          # transcendentals: |device - reference libm| <= 2 ulp
 COMPOSITE_RTOL = 1e-11  # whole tapes that chain transcendentals into arithmetic (ulp errors propagate)
@@ -37,12 +38,15 @@ def opcover_output_ops():
     return out_op
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("case_name", ["opcover", "opcover_special"])
-def test_operator_set_per_op(case_name):
+def test_operator_set_per_op(case_name, mode):
     tape = load_tape("opcover")
     case = load_case(case_name)
     N = case["N"]
-    got = CudaMap(tape, N)(case["in"])[0].reshape(N, -1)
+    m = CudaMap(tape, N, mode=mode)
+    assert m.f.info()["mode"] == capi.MODES[mode]
+    got = m(case["in"])[0].reshape(N, -1)
     want = case["out"][0].reshape(N, -1)
     out_op = opcover_output_ops()
     worst = {}
@@ -52,6 +56,16 @@ def test_operator_set_per_op(case_name):
             assert_bit_equal(got[:, j], want[:, j], "%s output %d (op %d, exact class)" % (case_name, j, op))
         else:
             u = ulp_diff(got[:, j], want[:, j])
+            if op == 86:
+                # The reference's erfinv (calculus.hpp:300-327) is not one libm call but two Newton steps
+                # y -= (erf(y)-x)/(2/sqrt(pi)*exp(-y*y)): the 1-ulp differences between CUDA's and glibc's
+                # erf/exp/log are divided by erf'(y), so the admissible distance is 2 ulp of each of those
+                # calls propagated through that quotient (plus 2 ulp of the result itself).
+                w = want[:, j]
+                with np.errstate(all="ignore"):
+                    dydx = 1.0 / (2.0 / np.sqrt(np.pi) * np.exp(-w * w))
+                    extra = 6 * np.spacing(1.0) * dydx / np.spacing(np.abs(w))
+                u = np.where(np.isfinite(extra), np.maximum(u - extra, 0.0), u)
             worst[j] = (op, float(u.max()))
             # chained transcendentals (e.g. log(fabs(a)+0.1)) still only contain ONE transcendental here
             assert u.max() <= ULP_TOL * ntrans, "%s output %d (op %d): %g ulp at a=%r b=%r c=%r (got %r want %r)" % (
@@ -60,33 +74,36 @@ def test_operator_set_per_op(case_name):
     print("worst ulp per transcendental output:", worst)
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", ["rocket_hess"])
-def test_exact_class_tapes_bit_exact_vs_reference(name):
+def test_exact_class_tapes_bit_exact_vs_reference(name, mode):
     tape, case = load_tape(name), load_case(name)
     ops = set(int(o) for o in tape["op"]) - {44, 45, 46}
     assert ops <= EXACT_OPS, ops - EXACT_OPS
-    outs = CudaMap(tape, case["N"])(case["in"])
+    outs = CudaMap(tape, case["N"], mode=mode)(case["in"])
     for j, (g, w) in enumerate(zip(outs, case["out"])):
         assert_bit_equal(g, w, "%s out%d" % (name, j))
 
 
 @pytest.mark.parametrize("name", ["cartpole", "cartpole1", "quad1", "quad", "quad_fwd", "quad_adj", "quad_jac",
                                   "quad1_jac", "mc", "mcstep", "mapnode"])
-def test_exactified_tapes_bit_exact_vs_oracle(name):
+@pytest.mark.parametrize("mode", MODES)
+def test_exactified_tapes_bit_exact_vs_oracle(name, mode):
     tape, case = exactify(load_tape(name)), load_case(name)
     N = min(case["N"], 200)
     ins = [a[:N * int(n)] for a, n in zip(case["in"], tape["nnz_in"])]
     want = oracle.map_eval(tape, N, ins)
-    got = CudaMap(tape, N)(ins)
+    got = CudaMap(tape, N, mode=mode)(ins)
     for j, (g, w) in enumerate(zip(got, want)):
         assert_bit_equal(g, w, "%s(exactified) out%d" % (name, j))
 
 
 @pytest.mark.parametrize("name", ["cartpole", "cartpole1", "quad1", "quad", "quad_fwd", "quad_adj", "quad_jac",
                                   "quad1_jac", "mc", "mcstep", "mapnode"])
-def test_composite_tapes_vs_reference(name):
+@pytest.mark.parametrize("mode", MODES)
+def test_composite_tapes_vs_reference(name, mode):
     tape, case = load_tape(name), load_case(name)
-    outs = CudaMap(tape, case["N"])(case["in"])
+    outs = CudaMap(tape, case["N"], mode=mode)(case["in"])
     for j, (g, w) in enumerate(zip(outs, case["out"])):
         scale = np.maximum(np.abs(w), 1.0)
         err = np.abs(g - w) / scale
@@ -100,7 +117,7 @@ def test_composite_tapes_vs_reference(name):
 def test_every_plan_gives_identical_bits(name, plans):
     """threads / instances-per-thread / shared-slot budget change where values live, never what is computed."""
     tape, case = load_tape(name), load_case(name)
-    t = CudaTape(tape)
+    t = CudaTape(tape, mode="interp")
     ref = None
     for (threads, ipt, S) in plans:
         t.set_plan(threads, ipt, S)
@@ -112,23 +129,26 @@ def test_every_plan_gives_identical_bits(name, plans):
                 assert_bit_equal(g, w, "%s plan %r out%d" % (name, (threads, ipt, S), j))
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("N", [1, 2, 31, 32, 33, 127, 128, 129, 255, 257, 1000])
-def test_ragged_batch_sizes(N):
+def test_ragged_batch_sizes(N, mode):
     tape, case = load_tape("cartpole1"), load_case("cartpole1")
     N = min(N, case["N"])
     ins = [a[:N * int(n)] for a, n in zip(case["in"], tape["nnz_in"])]
-    full = CudaMap(tape, case["N"])(case["in"])
-    got = CudaMap(tape, N)(ins)
+    t = CudaTape(tape, mode=mode)
+    full = CudaMap(t, case["N"])(case["in"])
+    got = CudaMap(t, N)(ins)
     for j in range(len(got)):
         assert_bit_equal(got[j], full[j][:N * int(tape["nnz_out"][j])], "N=%d out%d" % (N, j))
 
 
-def test_null_argument_reads_zero_null_result_skipped():
+@pytest.mark.parametrize("mode", MODES)
+def test_null_argument_reads_zero_null_result_skipped(mode):
     # reference semantics: sx_function.cpp:116-117
     tape, case = load_tape("mapnode"), load_case("mapnode")
     N = case["N"]
     ins = list(case["in"])
-    m = CudaMap(tape, N)
+    m = CudaMap(tape, N, mode=mode)
     zero = m([ins[0], np.zeros_like(ins[1]), ins[2], ins[3]])
     part = m([ins[0], None, ins[2], ins[3]], want=[True, False, True])
     assert part[1] is None
@@ -138,11 +158,12 @@ def test_null_argument_reads_zero_null_result_skipped():
     assert np.allclose(part[0], want[0], rtol=1e-13, atol=0)
 
 
-def test_device_pointer_api_soa_and_aos_layouts():
+@pytest.mark.parametrize("mode", MODES)
+def test_device_pointer_api_soa_and_aos_layouts(mode):
     import torch
     tape, case = load_tape("quad1"), load_case("quad1")
     N = case["N"]
-    t = CudaTape(tape)
+    t = CudaTape(tape, mode=mode)
     host = CudaMap(t, N)(case["in"])
     dev = torch.device("cuda:0")
     for layout in (LAYOUT_AOS, LAYOUT_SOA):
@@ -163,11 +184,13 @@ def test_device_pointer_api_soa_and_aos_layouts():
         assert t.last_kernel_ms() > 0
 
 
-def test_reduce_out_fixed_tree_and_reference_sum():
+@pytest.mark.parametrize("mode", MODES)
+def test_reduce_out_fixed_tree_and_reference_sum(mode):
     tape, case, ref = load_tape("mc"), load_case("mc"), load_case("mc_sum")
     N = case["N"]
-    per = CudaMap(tape, N)(case["in"])
-    red = CudaMap(tape, N, reduce_in=[0, 0], reduce_out=[1, 1])(case["in"])
+    t = CudaTape(tape, mode=mode)
+    per = CudaMap(t, N)(case["in"])
+    red = CudaMap(t, N, reduce_in=[0, 0], reduce_out=[1, 1])(case["in"])
     for j, nnz in enumerate((4, 1)):
         # (1) bit-exact against the documented summation tree applied to the per-instance device results
         assert_bit_equal(red[j], tree_sum(per[j].reshape(N, nnz)), "tree out%d" % j)
@@ -176,24 +199,27 @@ def test_reduce_out_fixed_tree_and_reference_sum():
         assert np.all(np.abs(red[j] - ref["out"][j]) <= bound), (red[j], ref["out"][j])
 
 
-def test_reduce_in_broadcast():
+@pytest.mark.parametrize("mode", MODES)
+def test_reduce_in_broadcast(mode):
     tape, case = load_tape("quad1"), load_case("quad1")
     N = 300
     u0 = case["in"][1][:4].copy()
     x = np.tile(case["in"][0][:12 * 100], 3)
-    full = CudaMap(tape, N)([x, np.tile(u0, N)])
-    bc = CudaMap(tape, N, reduce_in=[0, 1], reduce_out=[0])([x, u0])
+    t = CudaTape(tape, mode=mode)
+    full = CudaMap(t, N)([x, np.tile(u0, N)])
+    bc = CudaMap(t, N, reduce_in=[0, 1], reduce_out=[0])([x, u0])
     assert_bit_equal(bc[0], full[0])
 
 
-def test_large_batch_periodic_inputs_full_size():
+@pytest.mark.parametrize("mode", MODES)
+def test_large_batch_periodic_inputs_full_size(mode):
     """BASELINE size (N=1e6): inputs repeat with period P, so outputs must repeat bit-for-bit and the first
     period must match the reference golden -- a size-independent property."""
     tape, case = load_tape("cartpole"), load_case("cartpole")
     P, N = case["N"], 1_000_000
     reps = N // P
     ins = [np.tile(a, reps) for a in case["in"]]
-    out = CudaMap(tape, P * reps)(ins)[0].reshape(reps, -1)
+    out = CudaMap(tape, P * reps, mode=mode)(ins)[0].reshape(reps, -1)
     assert (out.view(np.uint64) == out[0].view(np.uint64)).all()
     err = np.abs(out[0] - case["out"][0]) / np.maximum(np.abs(case["out"][0]), 1.0)
     assert err.max() <= COMPOSITE_RTOL
@@ -203,3 +229,27 @@ def test_zero_batch_is_rejected_like_the_reference():
     from casadi_b200 import CcuError
     with pytest.raises(CcuError):
         CudaMap(load_tape("cartpole1"), 0)
+
+
+def test_interpreter_and_specialised_kernels_agree_bitwise():
+    """Same tape, same inputs: the two product paths must produce identical bits for exact-class tapes, and for
+    tapes with transcendentals too (both call the same CUDA math functions on the same operand values)."""
+    for name in ("quad", "rocket_hess", "mc"):
+        tape, case = load_tape(name), load_case(name)
+        a = CudaMap(tape, case["N"], mode="interp")(case["in"])
+        b = CudaMap(tape, case["N"], mode="jit")(case["in"])
+        for j, (x, y) in enumerate(zip(a, b)):
+            assert_bit_equal(x, y, "%s out%d interp vs jit" % (name, j))
+
+
+@pytest.mark.parametrize("seg,tile", [(200, 0), (1200, 256), (5000, 128), (64, 384)])
+def test_jit_segmentation_and_tiling_do_not_change_bits(seg, tile):
+    tape, case = load_tape("quad"), load_case("quad")
+    t = CudaTape(tape, mode="jit")
+    ref = CudaMap(t, case["N"])(case["in"])
+    t.set_jit_plan(seg_instr=seg, tile=tile)
+    info = t.info()
+    assert info["mode"] == capi.MODE_JIT and info["jit_segments"] >= 1
+    got = CudaMap(t, case["N"])(case["in"])
+    for j, (x, y) in enumerate(zip(got, ref)):
+        assert_bit_equal(x, y, "seg=%d tile=%d out%d" % (seg, tile, j))

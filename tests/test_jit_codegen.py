@@ -1,0 +1,124 @@
+"""CPU-only check of the tape specialiser's code generator (casadi_b200/csrc/jit.cpp).
+
+The CUDA source it emits for every segment is compiled here with g++ behind a few shims (__global__,
+blockIdx, __longlong_as_double ...) and executed on the host, one "thread" per instance, passing
+cross-segment values through the same [slot][instance] scratch the GPU uses.  With -ffp-contract=off and
+glibc's libm this reproduces the reference goldens BIT-FOR-BIT, transcendentals included, so segmentation,
+scratch-slot allocation, re-materialisation and the per-operator expressions are all pinned without a GPU.
+TEST INFRASTRUCTURE: nothing here is on the product path.
+"""
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from casadi_b200 import CudaTape, capi, load_case, load_tape
+from util import assert_bit_equal
+
+SHIM = r"""
+#include <cmath>
+#include <cstring>
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(...)
+static inline double __longlong_as_double(long long x) { double d; std::memcpy(&d, &x, 8); return d; }
+struct ccu_dim3 { unsigned x, y, z; };
+static ccu_dim3 blockIdx, blockDim, threadIdx;
+"""
+DRIVER = r"""
+extern "C" void run_seg(const ccu::IoDesc* io, long long inst0, long long n_tile, double* sc, long long sstride) {
+  blockDim.x = 1; threadIdx.x = 0;
+  for (long long t = 0; t < n_tile; ++t) { blockIdx.x = (unsigned)t; ccu_seg(*io, inst0, n_tile, sc, sstride); }
+}
+"""
+
+
+class IoDesc(ctypes.Structure):
+    _fields_ = [("in_", ctypes.c_void_p * 32), ("in_si", ctypes.c_longlong * 32), ("in_sk", ctypes.c_longlong * 32),
+                ("out", ctypes.c_void_p * 32), ("out_si", ctypes.c_longlong * 32), ("out_sk", ctypes.c_longlong * 32)]
+
+
+def run_generated(tape_name, case_name, seg_instr, nmax=40, null_in=None):
+    os.environ["CCU_JIT_SEG"] = str(seg_instr)
+    try:
+        t = CudaTape(load_tape(tape_name), device=-1)
+        sources = t.jit_sources()
+    finally:
+        del os.environ["CCU_JIT_SEG"]
+    case = load_case(case_name)
+    N = min(case["N"], nmax)
+    ins = [np.ascontiguousarray(a[:N * n]) for a, n in zip(case["in"], t.nnz_in)]
+    outs = [np.full(N * n, np.nan) for n in t.nnz_out]
+    io = IoDesc()
+    for j, a in enumerate(ins):
+        io.in_[j] = None if (a.size == 0 or (null_in is not None and j in null_in)) else a.ctypes.data
+        io.in_si[j], io.in_sk[j] = t.nnz_in[j], 1
+    for j, a in enumerate(outs):
+        io.out[j] = a.ctypes.data if a.size else None
+        io.out_si[j], io.out_sk[j] = t.nnz_out[j], 1
+    nslots = max([int(s.split("CCU_ST(")[k].split(",")[0]) for s in sources for k in range(1, len(s.split("CCU_ST(")))
+                  if s.split("CCU_ST(")[k][0].isdigit()] + [0]) + 1
+    scratch = np.full(nslots * N, np.nan)
+    with tempfile.TemporaryDirectory() as tmp:
+        procs = []
+        for k, src in enumerate(sources):
+            cpp = os.path.join(tmp, "seg%d.cpp" % k)
+            with open(cpp, "w") as f:
+                f.write(SHIM + src + DRIVER)
+            procs.append(subprocess.Popen(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17", "-w", cpp,
+                                           "-o", os.path.join(tmp, "seg%d.so" % k)]))
+        for p in procs:
+            assert p.wait() == 0
+        for k in range(len(sources)):
+            lib = ctypes.CDLL(os.path.join(tmp, "seg%d.so" % k))
+            lib.run_seg(ctypes.byref(io), ctypes.c_longlong(0), ctypes.c_longlong(N),
+                        scratch.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(N))
+    return len(sources), outs, [w[:N * n] for w, n in zip(case["out"], t.nnz_out)]
+
+
+@pytest.mark.parametrize("tape_name,case_name,seg", [
+    ("cartpole", "cartpole", 100000), ("cartpole", "cartpole", 50), ("quad1", "quad1", 64), ("quad1", "quad1", 17),
+    ("mcstep", "mcstep", 16), ("mapnode", "mapnode", 16), ("opcover", "opcover", 100000), ("opcover", "opcover", 16),
+    ("opcover", "opcover_special", 20), ("quad1_jac", "quad1_jac", 300), ("mc", "mc", 500)])
+def test_generated_segments_reproduce_reference_bits(tape_name, case_name, seg):
+    nseg, outs, want = run_generated(tape_name, case_name, seg, nmax=700 if case_name.startswith("opcover") else 24)
+    if seg < 1000:
+        assert nseg > 1
+    for j, (g, w) in enumerate(zip(outs, want)):
+        assert_bit_equal(g, w, "%s seg=%d out%d" % (case_name, seg, j))
+
+
+def test_generated_code_null_input_reads_zero():
+    import oracle
+    tape, case = load_tape("mapnode"), load_case("mapnode")
+    N = 20
+    _, outs, _ = run_generated("mapnode", "mapnode", 16, nmax=N, null_in={1})
+    ins = [a[:N * int(n)] for a, n in zip(case["in"], tape["nnz_in"])]
+    want = oracle.map_eval(tape, N, [ins[0], None, ins[2], ins[3]])
+    for g, w in zip(outs, want):
+        assert_bit_equal(g, w)
+
+
+def test_jit_plan_reports_cross_segment_traffic():
+    os.environ["CCU_JIT_SEG"] = "64"
+    try:
+        t = CudaTape(load_tape("quad1"), device=-1)
+        src = t.jit_sources()
+    finally:
+        del os.environ["CCU_JIT_SEG"]
+    assert len(src) >= 5
+    assert all("ccu_seg(" in s and "--fmad" not in s for s in src)
+    # every scratch slot that is read was written by an earlier segment
+    written = set()
+    for s in src:
+        for part in s.split("CCU_LD(")[1:]:
+            if part[0].isdigit():
+                assert int(part.split(")")[0]) in written
+        for part in s.split("CCU_ST(")[1:]:
+            if part[0].isdigit():
+                written.add(int(part.split(",")[0]))

@@ -45,3 +45,11 @@ def test_oracle_repsum_matches_reference_mapsum():
     outs = oracle.map_eval(tape, case["N"], case["in"])
     assert_bit_equal(oracle.repsum(outs[0], 4, case["N"]), ref["out"][0], "sum xT")
     assert_bit_equal(oracle.repsum(outs[1], 1, case["N"]), ref["out"][1], "sum J")
+
+
+def test_ulp_distance_helper_resolves_single_ulps():
+    from util import ulp_diff
+    a = np.array([1.0, 1.1935021221110558, -3.5, 0.0, np.nan, 1e300])
+    b = np.array([np.nextafter(1.0, 2.0), 1.193502122111056, np.nextafter(np.nextafter(-3.5, 0), 0), -0.0, np.nan, np.inf])
+    d = ulp_diff(a, b)
+    assert list(d[:5]) == [1.0, 1.0, 2.0, 0.0, 0.0] and d[5] == np.inf
