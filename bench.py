@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--n", type=int, default=10_000_000, help="instances per GPU per step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-interp", action="store_true")
     ap.add_argument("--cpu-n-per-core", type=int, default=2048)
     return ap.parse_args()
 
@@ -185,9 +186,12 @@ def main_cuda(args):
         dist.init_process_group("nccl", device_id=dev)
     N, K, W = args.n, args.steps, max(args.warmup, 3)
 
+    t_create = time.time()
     tF, tJ = CudaTape(load_tape("quad"), device=local), CudaTape(load_tape("quad_jac"), device=local)
+    t_create = time.time() - t_create
     iF, iJ = tF.info(), tJ.info()
     L = capi.lib()
+    mode_name = {capi.MODE_INTERP: "interp", capi.MODE_JIT: "jit"}
 
     # synthetic inputs, resident in HBM, SoA [k][instance] (the coalesced device layout of ccu_map_eval_device)
     g = torch.Generator(device=dev)
@@ -287,8 +291,21 @@ def main_cuda(args):
             raise SystemExit("bench.py: e2e parity check failed")
         e2e = {"value": world * N * Ke / dt, "unit": "evals/s", "steps": Ke,
                "h2d_bytes_per_step": 2 * 16 * 8 * N, "d2h_bytes_per_step": (12 + 114) * 8 * N,
-               "note": "ccu_map_eval_host on pinned AoS host buffers: H2D + kernel + D2H per call, host-clock timed"}
+               "note": "ccu_map_eval_host on pinned AoS host buffers (the reference's Map layout): chunked H2D | "
+                       "AoS->SoA, tape kernels, SoA->AoS | D2H pipeline inside the timed region, host-clock timed"}
         del hx, hu, hxf, hj0, hj1
+
+    # ---- the same workload on the interpreter kernel (the path that needs no NVRTC), reported beside the headline
+    interp = None
+    if iJ["mode"] == capi.MODE_JIT and world == 1 and not args.no_interp:
+        tF.set_mode(capi.MODE_INTERP); tJ.set_mode(capi.MODE_INTERP)
+        step(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream); step(); b.record(stream); torch.cuda.synchronize()
+        ims = a.elapsed_time(b)
+        interp = {"value": N / (ims * 1e-3), "unit": "evals/s", "ms_per_step": ims, "steps": 1,
+                  "plan_J": {k: iJ[k] for k in ("threads", "ipt", "slots_shared", "slots_global")}}
+        tF.set_mode(capi.MODE_JIT); tJ.set_mode(capi.MODE_JIT)
 
     if rank != 0:
         if world > 1:
@@ -309,13 +326,20 @@ def main_cuda(args):
     ach = flopsJ * N / (jac_ms * 1e-3) / 1e12
     hbm_ach = bytesJ * N / (jac_ms * 1e-3) / 1e9
     t_fp64, t_hbm = flopsJ / (p64 * 1e12), bytesJ / (hbm_peak * 1e9)
-    roofline = {"bound": "fp64" if t_fp64 >= t_hbm else "hbm", "kernel": "ccu_interp_kernel (quad_jac tape)",
+    kname = ("ccu_seg x%d per tile (quad_jac tape, specialised)" % iJ["jit_segments"]) if iJ["mode"] == capi.MODE_JIT \
+        else "ccu_interp_kernel (quad_jac tape)"
+    scratch_bytes = 8 * (iJ["jit_cross_loads"] + iJ["jit_cross_stores"]) if iJ["mode"] == capi.MODE_JIT \
+        else 8 * (iJ["spill_loads"] + iJ["spill_stores"])
+    roofline = {"bound": "fp64" if t_fp64 >= t_hbm else "hbm", "kernel": kname,
                 "achieved": ach, "peak": p64, "unit": "TFLOP/s", "frac": ach / p64,
                 "peak_source": "FP64 non-FMA issue rate measured live by ccu_fp64_issue_rate (DADD/s); contraction is off by contract",
                 "traffic": None, "kernel_ms": jac_ms, "flops_per_eval": flopsJ, "bytes_per_eval": bytesJ,
                 "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                         "peak_source": hbm_src},
-                "roofline_evals_per_s": 1.0 / max(t_fp64, t_hbm)}
+                "roofline_evals_per_s": 1.0 / max(t_fp64, t_hbm),
+                "scratch": {"bytes_per_eval": scratch_bytes, "achieved": scratch_bytes * N / (jac_ms * 1e-3) / 1e9,
+                            "unit": "GB/s", "frac_of_hbm_peak": scratch_bytes * N / (jac_ms * 1e-3) / 1e9 / hbm_peak,
+                            "note": "work-vector traffic of the 2625-live-value tape through HBM; not algorithmic bytes"}}
     cpu = None
     if not args.no_cpu and world == 1:
         try:
@@ -329,9 +353,12 @@ def main_cuda(args):
             "config": {"workload": WORKLOAD, "instances_per_gpu": N, "eval": "one instance through F and its Jacobian",
                        "layout": "SoA device-resident", "l2": "inputs+outputs (%.1f GB) larger than L2" % (
                            (iF["bytes_in"] + iF["bytes_out"] + bytesJ) * N / 1e9),
-                       "plan_F": {k: iF[k] for k in ("threads", "ipt", "slots_shared", "slots_global")},
-                       "plan_J": {k: iJ[k] for k in ("threads", "ipt", "slots_shared", "slots_global")}},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                       "mode": mode_name[iJ["mode"]], "tape_create_s": round(t_create, 2),
+                       "plan_F": {k: iF[k] for k in iF if k.startswith("jit_")} if iF["mode"] == capi.MODE_JIT else
+                       {k: iF[k] for k in ("threads", "ipt", "slots_shared", "slots_global")},
+                       "plan_J": {k: iJ[k] for k in iJ if k.startswith("jit_")} if iJ["mode"] == capi.MODE_JIT else
+                       {k: iJ[k] for k in ("threads", "ipt", "slots_shared", "slots_global")}},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "interpreter": interp, "gpu_launches": int(launches), "clocks": clocks,
             "parity_rel_err": perr}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -16,6 +17,7 @@
 #include "ccu_isa.h"
 #include "interp.cuh"
 #include "jit.hpp"
+#include "layout.cuh"
 #include "reduce.cuh"
 #include "tape_compile.hpp"
 
@@ -62,6 +64,26 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// staging of the host-pointer path (eval_host_impl): [slot] double buffering
+struct HostPipe {
+  bool ready = false;
+  cudaStream_t s[3] = {nullptr, nullptr, nullptr};  // H2D, compute, D2H
+  cudaEvent_t ev[2][3] = {};                        // per slot: H2D done, compute done, D2H done
+  std::vector<DevBuf> in_aos[2], in_soa[2], out_aos[2], out_soa[2];
+  std::vector<DevBuf> bcast;  // reduce_in operands (one instance)
+  DevBuf red;
+  void release() {
+    for (int b = 0; b < 2; ++b) {
+      for (auto* v : {&in_aos[b], &in_soa[b], &out_aos[b], &out_soa[b]}) for (auto& x : *v) x.release();
+      for (int k = 0; k < 3; ++k) if (ev[b][k]) cudaEventDestroy(ev[b][k]);
+    }
+    for (auto& x : bcast) x.release();
+    red.release();
+    for (int k = 0; k < 3; ++k) if (s[k]) cudaStreamDestroy(s[k]);
+    ready = false;
+  }
+};
+
 }  // namespace
 
 struct ccu_tape {
@@ -81,6 +103,7 @@ struct ccu_tape {
   // staging for the host-pointer path
   std::vector<DevBuf> d_in, d_out, d_part;
   DevBuf d_tmp;
+  HostPipe pipe;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
@@ -317,6 +340,7 @@ void ccu_tape_destroy(ccu_tape* t) {
     if (t->d_prog) cudaFree(t->d_prog);
     if (t->jit_built) ccu::jit_destroy(&t->jit);
     t->scratch.release(); t->d_tmp.release();
+    t->pipe.release();
     for (auto& b : t->d_in) b.release();
     for (auto& b : t->d_out) b.release();
     for (auto& b : t->d_part) b.release();
@@ -459,51 +483,116 @@ int ccu_map_eval_reduce_device(ccu_tape* t, ccu_int N, const double* const* d_ar
   return 0;
 }
 
+// Host-pointer evaluation (what CudaMap::eval calls): the batch is cut into chunks that flow through a
+// three-stage pipeline on three streams with double-buffered device staging,
+//     H2D (AoS)  ->  [AoS->SoA, tape kernels on SoA, SoA->AoS | block sums]  ->  D2H (AoS)
+// so the PCIe transfers of chunk c+1 / c-1 overlap the kernels of chunk c, and the tape kernels always run
+// on the coalesced SoA layout.  Chunks are multiples of kReduceBlock, so reduce_out block sums land at their
+// global positions and the summation tree is the same as for a single launch.
 static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res,
                           const int* reduce_in, const int* reduce_out) {
   if (check_eval_args(t, N)) return 1;
   CCU_CUDA(cudaSetDevice(t->device));
   const size_t n_in = t->nnz_in.size(), n_out = t->nnz_out.size();
-  std::vector<const double*> d_arg(n_in, nullptr);
-  std::vector<double*> d_res(n_out, nullptr);
-  cudaStream_t s = t->stream;
+  HostPipe& hp = t->pipe;
+  if (!hp.ready) {
+    for (int k = 0; k < 3; ++k) CCU_CUDA(cudaStreamCreateWithFlags(&hp.s[k], cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b)
+      for (int k = 0; k < 3; ++k) CCU_CUDA(cudaEventCreateWithFlags(&hp.ev[b][k], cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+      hp.in_aos[b].resize(n_in); hp.in_soa[b].resize(n_in); hp.out_aos[b].resize(n_out); hp.out_soa[b].resize(n_out);
+    }
+    hp.bcast.resize(n_in);
+    hp.ready = true;
+  }
+  cudaStream_t s_h2d = hp.s[0], s_cmp = hp.s[1], s_d2h = hp.s[2];
+  // chunk size: a multiple of kReduceBlock; ~8 chunks per call, between 64Ki and 1Mi instances
+  long long C = (N + 7) / 8;
+  if (const char* p = getenv("CCU_HOST_CHUNK")) C = atoll(p);
+  else C = std::max<long long>(1 << 16, std::min<long long>(1 << 20, C));
+  C = std::max<long long>(ccu::kReduceBlock, (C + ccu::kReduceBlock - 1) / ccu::kReduceBlock * ccu::kReduceBlock);
+  const long long nchunks = N > 0 ? (N + C - 1) / C : 0;
+  const long long nblocks = (N + ccu::kReduceBlock - 1) / ccu::kReduceBlock;
+  auto is_rin = [&](size_t j) { return reduce_in && reduce_in[j]; };
+  auto is_rout = [&](size_t j) { return reduce_out && reduce_out[j]; };
+  // broadcast (reduce_in) inputs: one instance, copied once
   for (size_t j = 0; j < n_in; ++j) {
-    if (!arg[j] || t->nnz_in[j] == 0) continue;
-    size_t cnt = static_cast<size_t>(t->nnz_in[j]) * ((reduce_in && reduce_in[j]) ? 1 : N);
-    if (cnt == 0) continue;
-    if (t->d_in[j].ensure(cnt)) return 1;
-    CCU_CUDA(cudaMemcpyAsync(t->d_in[j].p, arg[j], cnt * 8, cudaMemcpyHostToDevice, s));
-    d_arg[j] = t->d_in[j].p;
+    if (!is_rin(j) || !arg[j] || t->nnz_in[j] == 0) continue;
+    if (hp.bcast[j].ensure(static_cast<size_t>(t->nnz_in[j]))) return 1;
+    CCU_CUDA(cudaMemcpyAsync(hp.bcast[j].p, arg[j], t->nnz_in[j] * 8, cudaMemcpyHostToDevice, s_cmp));
   }
-  std::vector<DevBuf> red(n_out);
   for (size_t j = 0; j < n_out; ++j) {
-    if (!res[j] || t->nnz_out[j] == 0) continue;
-    const bool r = reduce_out && reduce_out[j];
-    size_t cnt = static_cast<size_t>(t->nnz_out[j]) * (r ? 1 : N);
-    if (cnt == 0) continue;
-    if (r) {
-      if (red[j].ensure(cnt)) return 1;
-      d_res[j] = red[j].p;
-    } else {
-      if (t->d_out[j].ensure(cnt)) return 1;
-      d_res[j] = t->d_out[j].p;
-    }
+    if (!is_rout(j) || !res[j] || t->nnz_out[j] == 0) continue;
+    if (t->d_part[j].ensure(static_cast<size_t>(std::max<long long>(nblocks, 1)) * t->nnz_out[j])) return 1;
   }
-  int rc;
-  if (reduce_in || reduce_out)
-    rc = ccu_map_eval_reduce_device(t, N, d_arg.data(), d_res.data(), reduce_in, reduce_out, CCU_LAYOUT_AOS, s);
-  else
-    rc = ccu_map_eval_device(t, N, d_arg.data(), d_res.data(), CCU_LAYOUT_AOS, s);
-  if (rc == 0) {
-    for (size_t j = 0; j < n_out && rc == 0; ++j) {
+  int rc = 0;
+  for (long long c = 0; c < nchunks && rc == 0; ++c) {
+    const int b = static_cast<int>(c & 1);
+    const long long i0 = c * C, n = std::min(C, N - i0);
+    std::vector<const double*> d_arg(n_in, nullptr);
+    std::vector<double*> d_res(n_out, nullptr);
+    // ---- stage 1: H2D (the staging of slot b is free once chunk c-2 has been computed)
+    CCU_CUDA(cudaStreamWaitEvent(s_h2d, hp.ev[b][1], 0));
+    for (size_t j = 0; j < n_in; ++j) {
+      if (!arg[j] || t->nnz_in[j] == 0) continue;
+      if (is_rin(j)) { d_arg[j] = hp.bcast[j].p; continue; }
+      const size_t cnt = static_cast<size_t>(t->nnz_in[j]) * C;
+      if (hp.in_aos[b][j].ensure(cnt) || hp.in_soa[b][j].ensure(cnt)) return 1;
+      CCU_CUDA(cudaMemcpyAsync(hp.in_aos[b][j].p, arg[j] + i0 * t->nnz_in[j], static_cast<size_t>(n) * t->nnz_in[j] * 8,
+                               cudaMemcpyHostToDevice, s_h2d));
+      d_arg[j] = hp.in_soa[b][j].p;
+    }
+    CCU_CUDA(cudaEventRecord(hp.ev[b][0], s_h2d));
+    // ---- stage 2: compute (the output staging of slot b is free once chunk c-2 has been copied back)
+    CCU_CUDA(cudaStreamWaitEvent(s_cmp, hp.ev[b][0], 0));
+    CCU_CUDA(cudaStreamWaitEvent(s_cmp, hp.ev[b][2], 0));
+    for (size_t j = 0; j < n_in; ++j) {
+      if (!arg[j] || t->nnz_in[j] == 0 || is_rin(j)) continue;
+      CCU_CUDA(ccu::launch_aos_to_soa(hp.in_aos[b][j].p, hp.in_soa[b][j].p, n, static_cast<int>(t->nnz_in[j]), n, s_cmp));
+      g_launches++;
+    }
+    for (size_t j = 0; j < n_out; ++j) {
+      if (!res[j] || t->nnz_out[j] == 0) continue;
+      const size_t cnt = static_cast<size_t>(t->nnz_out[j]) * C;
+      if (hp.out_soa[b][j].ensure(cnt)) return 1;
+      if (!is_rout(j) && hp.out_aos[b][j].ensure(cnt)) return 1;
+      d_res[j] = hp.out_soa[b][j].p;
+    }
+    ccu::IoDesc io;
+    fill_io(t, n, d_arg.data(), d_res.data(), CCU_LAYOUT_SOA, reduce_in, &io);
+    if (launch(t, io, n, s_cmp)) return 1;
+    for (size_t j = 0; j < n_out; ++j) {
       if (!d_res[j]) continue;
-      size_t cnt = static_cast<size_t>(t->nnz_out[j]) * ((reduce_out && reduce_out[j]) ? 1 : N);
-      cudaError_t e = cudaMemcpyAsync(res[j], d_res[j], cnt * 8, cudaMemcpyDeviceToHost, s);
-      if (e != cudaSuccess) rc = fail("D2H copy failed: %s", cudaGetErrorString(e));
+      const int nnz = static_cast<int>(t->nnz_out[j]);
+      if (is_rout(j)) {
+        CCU_CUDA(ccu::launch_block_sums(d_res[j], 1, n, n, nnz, t->d_part[j].p + (i0 / ccu::kReduceBlock) * nnz, s_cmp));
+      } else {
+        CCU_CUDA(ccu::launch_soa_to_aos(d_res[j], hp.out_aos[b][j].p, n, nnz, n, s_cmp));
+      }
+      g_launches++;
     }
+    CCU_CUDA(cudaEventRecord(hp.ev[b][1], s_cmp));
+    // ---- stage 3: D2H
+    CCU_CUDA(cudaStreamWaitEvent(s_d2h, hp.ev[b][1], 0));
+    for (size_t j = 0; j < n_out; ++j) {
+      if (!d_res[j] || is_rout(j)) continue;
+      CCU_CUDA(cudaMemcpyAsync(res[j] + i0 * t->nnz_out[j], hp.out_aos[b][j].p, static_cast<size_t>(n) * t->nnz_out[j] * 8,
+                               cudaMemcpyDeviceToHost, s_d2h));
+    }
+    CCU_CUDA(cudaEventRecord(hp.ev[b][2], s_d2h));
   }
-  cudaError_t e = cudaStreamSynchronize(s);
-  for (auto& b : red) b.release();
+  // reduced outputs: level-1 tree over the block sums, then a tiny D2H
+  for (size_t j = 0; j < n_out && rc == 0; ++j) {
+    if (!is_rout(j) || !res[j] || t->nnz_out[j] == 0) continue;
+    const int nnz = static_cast<int>(t->nnz_out[j]);
+    if (hp.red.ensure(static_cast<size_t>(nnz))) return 1;
+    CCU_CUDA(ccu::launch_tree(t->d_part[j].p, nblocks, nnz, hp.red.p, s_cmp));
+    g_launches++;
+    CCU_CUDA(cudaMemcpyAsync(res[j], hp.red.p, static_cast<size_t>(nnz) * 8, cudaMemcpyDeviceToHost, s_cmp));
+    CCU_CUDA(cudaStreamSynchronize(s_cmp));  // hp.red is reused by the next reduced output
+  }
+  cudaError_t e0 = cudaStreamSynchronize(s_h2d), e1 = cudaStreamSynchronize(s_cmp), e2 = cudaStreamSynchronize(s_d2h);
+  cudaError_t e = e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2);
   if (rc == 0 && e != cudaSuccess) rc = fail("evaluation failed on device: %s", cudaGetErrorString(e));
   return rc;
 }

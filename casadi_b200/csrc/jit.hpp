@@ -26,9 +26,9 @@
 namespace ccu {
 
 struct JitOptions {
-  int seg_instr = 1000;   // arithmetic instructions per segment
-  int threads = 128;      // CTA size
-  int min_blocks = 4;     // __launch_bounds__ second argument: 4 CTAs of 128 threads per SM = at most 128 registers (0 = up to 255)
+  int seg_instr = 800;    // arithmetic instructions per segment
+  int threads = 256;      // CTA size
+  int min_blocks = 2;     // __launch_bounds__ second argument: 2 CTAs of 256 threads per SM = at most 128 registers (0 = up to 255)
   int load_batch = 8;     // cross-segment live-ins are loaded in groups of this many (memory-level parallelism)
   int compile_threads = 0;  // 0 = hardware concurrency (max 32)
   long long tile = 0;     // instances per tile (0 = automatic)

@@ -253,3 +253,27 @@ def test_jit_segmentation_and_tiling_do_not_change_bits(seg, tile):
     got = CudaMap(t, case["N"])(case["in"])
     for j, (x, y) in enumerate(zip(got, ref)):
         assert_bit_equal(x, y, "seg=%d tile=%d out%d" % (seg, tile, j))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_host_path_chunked_pipeline_matches_single_chunk(mode, monkeypatch):
+    """ccu_map_eval_host cuts the batch into chunks (H2D / compute / D2H overlap); chunking must not change a bit,
+    nor the reduce_out summation tree (chunks are multiples of the 1024-instance reduction block)."""
+    tape, case = load_tape("mc"), load_case("mc")
+    P, reps = case["N"], 26
+    N = P * reps - 37  # ragged last chunk
+    ins = [np.tile(a, reps)[:N * int(n)] for a, n in zip(case["in"], tape["nnz_in"])]
+    t = CudaTape(tape, mode=mode)
+    monkeypatch.setenv("CCU_HOST_CHUNK", "1048576")
+    one = CudaMap(t, N)(ins)
+    red_one = CudaMap(t, N, reduce_in=[0, 0], reduce_out=[1, 1])(ins)
+    monkeypatch.setenv("CCU_HOST_CHUNK", "1024")
+    many = CudaMap(t, N)(ins)
+    red_many = CudaMap(t, N, reduce_in=[0, 0], reduce_out=[1, 1])(ins)
+    for j in range(2):
+        assert_bit_equal(many[j], one[j], "chunked out%d" % j)
+        assert_bit_equal(red_many[j], red_one[j], "chunked reduce out%d" % j)
+        assert_bit_equal(red_many[j], tree_sum(one[j].reshape(N, -1)), "tree out%d" % j)
+    # first period against the reference golden
+    err = np.abs(many[1][:P] - case["out"][1]) / np.maximum(np.abs(case["out"][1]), 1.0)
+    assert err.max() <= COMPOSITE_RTOL
