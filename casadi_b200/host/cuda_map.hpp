@@ -1,0 +1,81 @@
+/*
+ * CudaMap -- `Function::map(n, "cuda")`: a fourth Map parallelization next to "serial", "openmp" and
+ * "thread" (casadi/core/map.hpp:39-330).
+ *
+ * This file and cuda_map.cpp are NEW files for casadi/core/ (they are not copies of reference code); the
+ * reference-side change is casadi_map_cuda.patch (a "cuda" branch in Map::create, a "CudaMap" branch in
+ * Map::deserialize, two CMake lines).  See INTEGRATION.md.
+ *
+ * CudaMap exports the SXFunction instruction tape of the mapped function through the public accessors
+ * (function.hpp:1114-1138), hands it to libcasadi_cuda.so through the C ABI of include/casadi_cuda.h
+ * (dlopen'ed on first use, so libcasadi itself gains no CUDA dependency) and evaluates all n instances
+ * on the GPU.  There is no CPU fallback: functions that cannot run on the device fail at init.
+ */
+#ifndef CASADI_CUDA_MAP_HPP
+#define CASADI_CUDA_MAP_HPP
+
+#include "map.hpp"
+
+/// \cond INTERNAL
+
+namespace casadi {
+
+  /** Memory object of a CudaMap: one compiled tape (device program, staging buffers, streams) per
+      checked-out memory, so concurrent evaluations on distinct memory objects do not share state
+      (function_internal.hpp:184-194). */
+  struct CASADI_EXPORT CudaMapMemory : public FunctionMemory {
+    void* tape;
+    CudaMapMemory() : tape(nullptr) {}
+  };
+
+  class CASADI_EXPORT CudaMap : public Map {
+    friend class Map;
+  public:
+    // Constructor (use Map::create("cuda", f, n))
+    CudaMap(const std::string& name, const Function& f, casadi_int n);
+
+    ~CudaMap() override;
+
+    std::string class_name() const override {return "CudaMap";}
+
+    bool is_a(const std::string& type, bool recursive) const override;
+
+    /// Type of parallellization: keeps Map::get_forward/get_reverse (map.cpp:226,280) on the GPU
+    std::string parallelization() const override { return "cuda"; }
+
+    void init(const Dict& opts) override;
+
+    /// Evaluate the function numerically: all n instances on the device
+    int eval(const double** arg, double** res, casadi_int* iw, double* w, void* mem) const override;
+
+    /// No C code generation for the device path
+    bool has_codegen() const override { return false;}
+
+    void* alloc_mem() const override { return new CudaMapMemory(); }
+    int init_mem(void* mem) const override;
+    void free_mem(void *mem) const override;
+
+    /** The exported tape of the mapped function (reference layout, sx_function.hpp:37-44) */
+    struct Tape {
+      std::vector<int> op, i0, i1, i2;
+      std::vector<double> d;
+      casadi_int sz_w;
+      std::vector<casadi_int> nnz_in, nnz_out;
+    };
+    static Tape export_tape(const Function& f);
+
+  protected:
+    explicit CudaMap(DeserializingStream& s);
+
+  private:
+    // The SX function whose tape runs on the device (f_ itself, or f_.expand() for an MX function)
+    Function sx_;
+    Tape tape_;
+    int device_;
+    void export_function();
+  };
+
+} // namespace casadi
+/// \endcond
+
+#endif // CASADI_CUDA_MAP_HPP

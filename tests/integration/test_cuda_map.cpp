@@ -1,0 +1,249 @@
+// Integration test (TEST INFRASTRUCTURE): `f.map(N, "cuda")` through the reference's own public C++ API, in a
+// libcasadi.so relinked with the patched Map::create and the new CudaMap (build_integration.py).
+// Mirrors the reference's map tests: test/python/function.py:658-757 (test_map_node: all parallelizations +
+// AD), :938-1009 (mapaccum), check_serialize (helpers.py:1016-1029) and the error behaviour of map.cpp:49.
+//
+//   test_cuda_map            full run (needs a CUDA device and libcasadi_cuda.so)
+//   test_cuda_map --no-gpu   host-side checks only: dispatch, tape export, loud failure without a device
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <unistd.h>
+
+#include "models.hpp"
+
+using namespace casadi;
+
+static int g_fail = 0;
+#define CHECK(cond, msg) do { if (!(cond)) { printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, std::string(msg).c_str()); ++g_fail; } } while (0)
+
+static double ulp_dist(double a, double b) {
+  if (a == b || (std::isnan(a) && std::isnan(b))) return 0;
+  if (!std::isfinite(a) || !std::isfinite(b)) return INFINITY;
+  long long x, y;
+  std::memcpy(&x, &a, 8); std::memcpy(&y, &b, 8);
+  if (x < 0) x = static_cast<long long>(0x8000000000000000ull) - x;
+  if (y < 0) y = static_cast<long long>(0x8000000000000000ull) - y;
+  return std::fabs(static_cast<double>(x - y));
+}
+
+struct Buffers {
+  std::vector<std::vector<double>> in, out;
+  std::vector<const double*> arg;
+  std::vector<double*> res;
+  std::vector<casadi_int> iw;
+  std::vector<double> w;
+};
+
+// evaluate F through the buffer API (function.cpp:1708-1738) on given inputs
+static std::vector<std::vector<double>> eval(const Function& F, const std::vector<std::vector<double>>& in,
+                                             const std::vector<bool>& null_in = {}, const std::vector<bool>& null_out = {}) {
+  Buffers b;
+  b.in = in;
+  b.arg.assign(F.sz_arg(), nullptr);
+  b.res.assign(F.sz_res(), nullptr);
+  b.iw.resize(F.sz_iw());
+  b.w.resize(F.sz_w());
+  b.out.resize(F.n_out());
+  for (casadi_int j = 0; j < F.n_in(); ++j)
+    b.arg[j] = (j < (casadi_int)null_in.size() && null_in[j]) ? nullptr : b.in[j].data();
+  for (casadi_int j = 0; j < F.n_out(); ++j) {
+    b.out[j].assign(F.nnz_out(j), -777.0);
+    b.res[j] = (j < (casadi_int)null_out.size() && null_out[j]) ? nullptr : b.out[j].data();
+  }
+  int flag = F(b.arg.data(), b.res.data(), b.iw.data(), b.w.data(), 0);
+  CHECK(flag == 0, "evaluation of " + F.name() + " returned " + str(flag));
+  return b.out;
+}
+
+static std::vector<std::vector<double>> random_inputs(const Function& F, unsigned seed, double lo, double hi) {
+  std::mt19937_64 g(seed);
+  std::vector<std::vector<double>> in(F.n_in());
+  for (casadi_int j = 0; j < F.n_in(); ++j) {
+    in[j].resize(F.nnz_in(j));
+    for (auto& v : in[j]) v = lo + (hi - lo) * std::generate_canonical<double, 53>(g);
+  }
+  return in;
+}
+
+// max ulp distance over all outputs
+static double compare(const std::vector<std::vector<double>>& a, const std::vector<std::vector<double>>& b, double* relerr) {
+  double worst = 0;
+  *relerr = 0;
+  CHECK(a.size() == b.size(), "output count");
+  for (size_t j = 0; j < a.size(); ++j) {
+    CHECK(a[j].size() == b[j].size(), "output size");
+    for (size_t k = 0; k < a[j].size(); ++k) {
+      worst = std::max(worst, ulp_dist(a[j][k], b[j][k]));
+      *relerr = std::max(*relerr, std::fabs(a[j][k] - b[j][k]) / std::max(1.0, std::fabs(b[j][k])));
+    }
+  }
+  return worst;
+}
+
+static void host_side_checks() {
+  using namespace ccu_models;
+  // the tape export reads the same tape SXFunction::eval runs (sx_function.cpp:72-127)
+  Function f = cartpole(4);
+  CHECK(f.n_instructions() == 522, "cartpole tape length " + str(f.n_instructions()));
+  // "serial" etc. are untouched by the patch; unknown strings still raise (map.cpp:49)
+  Function s = f.map(3, "serial");
+  CHECK(s.class_name() == "Map", s.class_name());
+  bool threw = false;
+  try { f.map(3, "no_such_mode"); } catch (std::exception& e) { threw = std::string(e.what()).find("Unknown parallelization") != std::string::npos; }
+  CHECK(threw, "unknown parallelization must raise");
+  // free variables are rejected when the map is created
+  SX x = SX::sym("x"), p = SX::sym("p");
+  Function ff("ff", {x}, {x * p}, Dict{{"allow_free", true}});
+  threw = false;
+  try { ff.map(4, "cuda"); } catch (std::exception& e) { threw = std::string(e.what()).find("free variables") != std::string::npos; }
+  CHECK(threw, "free variables must be rejected at creation");
+  // an MX function with a Linsol call cannot be expanded: loud failure, no fallback
+  threw = false;
+  try { kkt_solve("ldl").map(4, "cuda"); } catch (std::exception& e) { threw = std::string(e.what()).find("cannot be expanded") != std::string::npos; }
+  CHECK(threw, "non-expandable MX function must be rejected");
+}
+
+static void no_gpu_checks() {
+  using namespace ccu_models;
+  bool threw = false;
+  std::string msg;
+  try { cartpole(1).map(4, "cuda"); } catch (std::exception& e) { threw = true; msg = e.what(); }
+  CHECK(threw, "without a CUDA device the map must fail at creation");
+  CHECK(msg.find("no CPU fallback") != std::string::npos || msg.find("Cannot load") != std::string::npos, msg);
+  printf("no-gpu message: %s\n", msg.substr(0, 300).c_str());
+}
+
+static void gpu_checks() {
+  using namespace ccu_models;
+  // ---- test_map_node (function.py:658-696): all parallelizations, n=2 and a larger n
+  Function f = map_node_fun();
+  for (casadi_int n : {2, 50, 1000}) {
+    Function ref = f.map(n, "serial");
+    auto in = random_inputs(ref, 7, 0.1, 1.0);
+    auto want = eval(ref, in);
+    for (std::string par : {"openmp", "thread", "cuda"}) {
+      if (par == "thread" && n > 50) continue;
+      Function F = f.map(n, par);
+      if (par == "cuda") {
+        CHECK(F.class_name() == "CudaMap", F.class_name());
+        CHECK(F.is_a("Map", true), "CudaMap is_a Map");
+        CHECK(F.name() == "cudamap" + str(n) + "_f", F.name());
+        for (casadi_int j = 0; j < F.n_in(); ++j) CHECK(F.sparsity_in(j) == ref.sparsity_in(j), "sparsity_in");
+        for (casadi_int j = 0; j < F.n_out(); ++j) CHECK(F.sparsity_out(j) == ref.sparsity_out(j), "sparsity_out");
+      }
+      auto got = eval(F, in);
+      double rel;
+      double u = compare(got, want, &rel);
+      // outputs 0 and 2 are exact-class (mtimes+add, division); output 1 is sin(): <= 2 ulp
+      double r0, r2;
+      std::vector<std::vector<double>> g0{got[0], got[2]}, w0{want[0], want[2]};
+      CHECK(compare(g0, w0, &r0) == 0, par + ": exact-class outputs must be bit-identical");
+      CHECK(u <= 2, par + ": sin output differs by " + str(u) + " ulp");
+      (void)r2;
+    }
+  }
+  // ---- null argument / null result (sx_function.cpp:116-117) through the map
+  {
+    casadi_int n = 20;
+    Function ref = f.map(n, "serial"), F = f.map(n, "cuda");
+    auto in = random_inputs(ref, 8, 0.1, 1.0);
+    auto want = eval(ref, in, {false, true, false, false}, {false, true, false});
+    auto got = eval(F, in, {false, true, false, false}, {false, true, false});
+    double rel;
+    CHECK(compare(got, want, &rel) == 0, "null arg/res");
+    CHECK(got[1][0] == -777.0, "null result must not be written");
+  }
+  // ---- derivatives of the map stay on the device: Map::get_forward/get_reverse map the derivative function
+  //      with parallelization() (map.cpp:226,280)
+  {
+    casadi_int n = 6;
+    Function ref = f.map(n, "serial"), F = f.map(n, "cuda");
+    for (int rev = 0; rev < 2; ++rev) {
+      Function dref = rev ? ref.reverse(2) : ref.forward(2);
+      Function dF = rev ? F.reverse(2) : F.forward(2);
+      std::vector<std::string> calls;
+      bool has_cuda = false;
+      for (auto& nm : dF.get_function()) has_cuda = has_cuda || dF.get_function(nm).class_name() == "CudaMap";
+      CHECK(has_cuda, std::string(rev ? "reverse" : "forward") + " of a cuda map must call a CudaMap");
+      auto in = random_inputs(dref, 9 + rev, 0.1, 1.0);
+      auto want = eval(dref, in), got = eval(dF, in);
+      double rel;
+      compare(got, want, &rel);
+      CHECK(rel <= 1e-13, std::string(rev ? "reverse" : "forward") + " sensitivities rel err " + str(rel));
+    }
+  }
+  // ---- serialization round trip (check_serialize, helpers.py:1016-1029; Map::deserialize map.cpp:110-122)
+  {
+    Function F = f.map(5, "cuda");
+    Function G = Function::deserialize(F.serialize());
+    CHECK(G.class_name() == "CudaMap", "deserialized class " + G.class_name());
+    auto in = random_inputs(F, 11, 0.1, 1.0);
+    double rel;
+    CHECK(compare(eval(G, in), eval(F, in), &rel) == 0, "deserialized map differs");
+  }
+  // ---- BASELINE config 0: cart-pole RK4, N = 1e5, against the serial map
+  {
+    casadi_int n = 100000;
+    Function c = cartpole(4);
+    Function ref = c.map(n, "serial"), F = c.map(n, "cuda");
+    auto in = random_inputs(ref, 1, -0.5, 0.5);
+    double rel;
+    compare(eval(F, in), eval(ref, in), &rel);
+    CHECK(rel <= 1e-12, "cartpole N=1e5 rel err " + str(rel));
+  }
+  // ---- exact-class tape (rocket hess_lag): bit-identical to the serial map
+  {
+    casadi_int n = 64;
+    Function h = rocket_hess_lag(20);
+    Function ref = h.map(n, "serial"), F = h.map(n, "cuda");
+    auto in = random_inputs(ref, 3, 0.5, 1.5);
+    double rel;
+    CHECK(compare(eval(F, in), eval(ref, in), &rel) == 0, "hess_lag must be bit-identical");
+  }
+  // ---- mapaccum tower (function.py:938-1009): an MXFunction that CudaMap expands to one SX tape
+  {
+    Function acc = mc_leaf().mapaccum(10);
+    CHECK(acc.class_name() == "MXFunction", acc.class_name());
+    casadi_int n = 300;
+    Function ref = acc.map(n, "serial"), F = acc.map(n, "cuda");
+    auto in = random_inputs(ref, 4, -1, 1);
+    double rel;
+    compare(eval(F, in), eval(ref, in), &rel);
+    CHECK(rel <= 1e-13, "mapaccum rel err " + str(rel));
+  }
+  // ---- map with reductions (function.cpp:797-818): HorzRepmat/HorzRepsum around the Map node
+  {
+    casadi_int n = 40;
+    Function g = mc_leaf();
+    Function ref = g.map("r", "serial", n, std::vector<casadi_int>{0}, std::vector<casadi_int>{1});
+    Function F = g.map("r", "cuda", n, std::vector<casadi_int>{0}, std::vector<casadi_int>{1});
+    auto in = random_inputs(ref, 5, -1, 1);
+    double rel;
+    compare(eval(F, in), eval(ref, in), &rel);
+    CHECK(rel <= 1e-13, "map with reduce_in/out rel err " + str(rel));
+  }
+}
+
+int main(int argc, char** argv) {
+  bool no_gpu = argc > 1 && std::string(argv[1]) == "--no-gpu";
+  {  // Linsol plugins live next to libcasadi.so: <exe dir>/../lib
+    char buf[4096];
+    ssize_t len = readlink("/proc/self/exe", buf, sizeof(buf) - 1);
+    if (len > 0) {
+      std::string p(buf, len);
+      p = p.substr(0, p.rfind('/'));
+      GlobalOptions::setCasadiPath(p.substr(0, p.rfind('/')) + "/lib");
+    }
+  }
+  try {
+    host_side_checks();
+    if (no_gpu) no_gpu_checks(); else gpu_checks();
+  } catch (std::exception& e) {
+    printf("FAIL: unexpected exception: %s\n", e.what());
+    return 1;
+  }
+  printf(g_fail ? "%d check(s) FAILED\n" : "integration ok%.0d\n", g_fail);
+  return g_fail ? 1 : 0;
+}
