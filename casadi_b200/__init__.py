@@ -8,4 +8,5 @@ Package layout
 """
 from .capi import CcuError, LAYOUT_AOS, LAYOUT_SOA  # noqa: F401
 from .cuda_map import CudaMap, CudaTape  # noqa: F401
+from .linsol import CudaLinsol  # noqa: F401
 from .tapeio import load_case, load_tape  # noqa: F401

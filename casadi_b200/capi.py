@@ -43,6 +43,23 @@ SYMBOLS = {
     "ccu_map_eval_device": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, ctypes.c_int, c_vp]),
     "ccu_map_eval_reduce_host": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_i_p, c_i_p]),
     "ccu_map_eval_reduce_device": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_i_p, c_i_p, ctypes.c_int, c_vp]),
+    "ccu_builder_create": (c_vp, []),
+    "ccu_builder_destroy": (None, [c_vp]),
+    "ccu_builder_const": (c_ll, [c_vp, ctypes.c_double]),
+    "ccu_builder_input": (c_ll, [c_vp, c_ll, c_ll]),
+    "ccu_builder_op": (c_ll, [c_vp, ctypes.c_int, c_ll, c_ll]),
+    "ccu_builder_output": (ctypes.c_int, [c_vp, c_ll, c_ll, c_ll]),
+    "ccu_builder_ldl": (ctypes.c_int, [c_vp, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll, c_ll_p]),
+    "ccu_builder_qr": (ctypes.c_int, [c_vp, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll, ctypes.c_int,
+                                      ctypes.c_double, c_ll_p]),
+    "ccu_builder_mtimes": (ctypes.c_int, [c_vp, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll_p]),
+    "ccu_builder_finish": (c_vp, [c_vp, c_ll, c_ll_p, c_ll, c_ll_p, ctypes.c_int]),
+    "ccu_ldl_create": (c_vp, [c_ll_p, c_ll_p, c_ll_p, c_ll, ctypes.c_int]),
+    "ccu_qr_create": (c_vp, [c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll, ctypes.c_int, ctypes.c_double, ctypes.c_int]),
+    "ccu_linsol_destroy": (None, [c_vp]),
+    "ccu_linsol_tape": (c_vp, [c_vp]),
+    "ccu_linsol_solve_host": (ctypes.c_int, [c_vp, c_ll, c_d_p, c_d_p, c_d_p, c_ll_p]),
+    "ccu_linsol_solve_device": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]),
     "ccu_tape_last_kernel_ms": (ctypes.c_int, [c_vp, c_d_p]),
     "ccu_launch_count": (c_ll, []),
     "ccu_fp64_issue_rate": (ctypes.c_int, [ctypes.c_int, c_d_p]),

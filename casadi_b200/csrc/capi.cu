@@ -19,6 +19,7 @@
 #include "jit.hpp"
 #include "layout.cuh"
 #include "reduce.cuh"
+#include "tape_builder.hpp"
 #include "tape_compile.hpp"
 
 namespace {
@@ -604,6 +605,175 @@ int ccu_map_eval_host(ccu_tape* t, ccu_int N, const double* const* arg, double* 
 int ccu_map_eval_reduce_host(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res,
                              const int* reduce_in, const int* reduce_out) {
   return eval_host_impl(t, N, arg, res, reduce_in, reduce_out);
+}
+
+// ---------------------------------------------------------------------------------------- tape builder
+struct ccu_builder {
+  ccu::TapeBuilder b;
+};
+
+struct ccu_linsol {
+  ccu_tape* tape = nullptr;
+  ccu_int n = 0, nnz_a = 0, nrhs = 0;
+  int kind = 0;  // 0 = LDL, 1 = QR
+};
+
+namespace {
+ccu_int pattern_nnz(const ccu_int* sp) { return sp[2 + sp[1]]; }
+bool pattern_ok(const ccu_int* sp) {
+  if (!sp || sp[0] < 0 || sp[1] < 0) return false;
+  const ccu_int ncol = sp[1];
+  const ccu_int* ci = sp + 2;
+  if (ci[0] != 0) return false;
+  for (ccu_int c = 0; c < ncol; ++c) if (ci[c + 1] < ci[c]) return false;
+  const ccu_int* r = sp + 2 + ncol + 1;
+  for (ccu_int k = 0; k < ci[ncol]; ++k) if (r[k] < 0 || r[k] >= sp[0]) return false;
+  return true;
+}
+bool perm_ok(const ccu_int* p, ccu_int n) {
+  if (!p) return false;
+  std::vector<char> seen(static_cast<size_t>(n), 0);
+  for (ccu_int i = 0; i < n; ++i) {
+    if (p[i] < 0 || p[i] >= n || seen[p[i]]) return false;
+    seen[p[i]] = 1;
+  }
+  return true;
+}
+bool ids_ok(const ccu_builder* b, const ccu_int* v, ccu_int n) {
+  for (ccu_int i = 0; i < n; ++i) if (v[i] < 0 || v[i] >= b->b.n_values()) return false;
+  return true;
+}
+}  // namespace
+
+ccu_builder* ccu_builder_create(void) { return new ccu_builder(); }
+void ccu_builder_destroy(ccu_builder* b) { delete b; }
+ccu_int ccu_builder_const(ccu_builder* b, double c) { return b ? b->b.constant(c) : -1; }
+ccu_int ccu_builder_input(ccu_builder* b, ccu_int idx, ccu_int nz) {
+  if (!b || idx < 0 || nz < 0) { fail("ccu_builder_input: invalid arguments"); return -1; }
+  return b->b.input(idx, nz);
+}
+ccu_int ccu_builder_op(ccu_builder* b, int op, ccu_int x, ccu_int y) {
+  if (!b || x < 0 || x >= b->b.n_values() || y >= b->b.n_values()) { fail("ccu_builder_op: invalid operand"); return -1; }
+  return b->b.op(op, x, y);
+}
+int ccu_builder_output(ccu_builder* b, ccu_int idx, ccu_int nz, ccu_int v) {
+  if (!b || idx < 0 || nz < 0 || v < 0 || v >= b->b.n_values()) return fail("ccu_builder_output: invalid arguments");
+  b->b.output(idx, nz, v);
+  return 0;
+}
+
+int ccu_builder_ldl(ccu_builder* b, const ccu_int* sp_a, const ccu_int* sp_lt, const ccu_int* p, const ccu_int* a,
+                    ccu_int* x, ccu_int nrhs, ccu_int* zero_pivots) {
+  if (!b || !pattern_ok(sp_a) || !pattern_ok(sp_lt) || sp_a[0] != sp_a[1] || sp_lt[0] != sp_a[0] || sp_lt[1] != sp_a[1] ||
+      !perm_ok(p, sp_a[1]) || !a || !x || nrhs < 0)
+    return fail("ccu_builder_ldl: invalid pattern, permutation or arguments");
+  const ccu_int n = sp_a[1];
+  if (!ids_ok(b, a, pattern_nnz(sp_a)) || !ids_ok(b, x, n * nrhs)) return fail("ccu_builder_ldl: invalid value handle");
+  std::vector<ccu::TapeBuilder::V> lt, d;
+  b->b.ldl(sp_a, a, sp_lt, &lt, &d, p);
+  b->b.ldl_solve(x, nrhs, sp_lt, lt.data(), d.data(), p);
+  if (zero_pivots) *zero_pivots = b->b.ldl_zero_pivots(d.data(), n);
+  return 0;
+}
+
+int ccu_builder_qr(ccu_builder* b, const ccu_int* sp_a, const ccu_int* sp_v, const ccu_int* sp_r, const ccu_int* prinv,
+                   const ccu_int* pc, const ccu_int* a, ccu_int* x, ccu_int nrhs, int tr, double eps, ccu_int* nullity) {
+  if (!b || !pattern_ok(sp_a) || !pattern_ok(sp_v) || !pattern_ok(sp_r) || sp_a[0] != sp_a[1] || sp_v[1] != sp_a[1] ||
+      sp_r[1] != sp_a[1] || sp_v[0] < sp_a[0] || !perm_ok(pc, sp_a[1]) || !prinv || !a || !x || nrhs < 0)
+    return fail("ccu_builder_qr: invalid pattern, permutation or arguments");
+  const ccu_int n = sp_a[1];
+  for (ccu_int i = 0; i < sp_a[0]; ++i) if (prinv[i] < 0 || prinv[i] >= sp_v[0]) return fail("ccu_builder_qr: invalid prinv");
+  if (!ids_ok(b, a, pattern_nnz(sp_a)) || !ids_ok(b, x, n * nrhs)) return fail("ccu_builder_qr: invalid value handle");
+  std::vector<ccu::TapeBuilder::V> v, r, beta;
+  b->b.qr(sp_a, a, sp_v, &v, sp_r, &r, &beta, prinv, pc);
+  b->b.qr_solve(x, nrhs, tr != 0, sp_v, v.data(), sp_r, r.data(), beta.data(), prinv, pc);
+  if (nullity) *nullity = b->b.qr_nullity(r.data(), sp_r, eps);
+  return 0;
+}
+
+int ccu_builder_mtimes(ccu_builder* b, const ccu_int* x, const ccu_int* sp_x, const ccu_int* y, const ccu_int* sp_y,
+                       ccu_int* z, const ccu_int* sp_z) {
+  if (!b || !pattern_ok(sp_x) || !pattern_ok(sp_y) || !pattern_ok(sp_z) || sp_x[1] != sp_y[0] || sp_z[0] != sp_x[0] ||
+      sp_z[1] != sp_y[1] || !x || !y || !z)
+    return fail("ccu_builder_mtimes: inconsistent patterns");
+  if (!ids_ok(b, x, pattern_nnz(sp_x)) || !ids_ok(b, y, pattern_nnz(sp_y)) || !ids_ok(b, z, pattern_nnz(sp_z)))
+    return fail("ccu_builder_mtimes: invalid value handle");
+  b->b.mtimes(x, sp_x, y, sp_y, z, sp_z);
+  return 0;
+}
+
+ccu_tape* ccu_builder_finish(ccu_builder* b, ccu_int n_in, const ccu_int* nnz_in, ccu_int n_out, const ccu_int* nnz_out,
+                             int device) {
+  if (!b) { fail("null builder"); return nullptr; }
+  std::vector<long long> ni(nnz_in, nnz_in + (n_in > 0 ? n_in : 0)), no(nnz_out, nnz_out + (n_out > 0 ? n_out : 0));
+  ccu::TapeSource s = b->b.source(ni, no);
+  return ccu_tape_create(s.n_instr, s.op, s.i0, s.i1, s.i2, s.d, s.sz_w, n_in, nnz_in, n_out, nnz_out, device);
+}
+
+// ------------------------------------------------------------------------- batched linear solves (K3/K4)
+static ccu_linsol* linsol_finish(ccu_builder& B, int kind, ccu_int n, ccu_int nnz_a, ccu_int nrhs, const ccu_int* x,
+                                 ccu_int flag_count, int device) {
+  for (ccu_int i = 0; i < n * nrhs; ++i) B.b.output(0, i, x[i]);
+  B.b.output(1, 0, B.b.op(22 /* OP_NE */, flag_count, B.b.constant(0.0)));
+  const ccu_int nnz_in[2] = {nnz_a, n * nrhs}, nnz_out[2] = {n * nrhs, 1};
+  ccu_tape* t = ccu_builder_finish(&B, 2, nnz_in, 2, nnz_out, device);
+  if (!t) return nullptr;
+  ccu_linsol* ls = new ccu_linsol();
+  ls->tape = t; ls->n = n; ls->nnz_a = nnz_a; ls->nrhs = nrhs; ls->kind = kind;
+  return ls;
+}
+
+ccu_linsol* ccu_ldl_create(const ccu_int* sp_a, const ccu_int* sp_lt, const ccu_int* p, ccu_int nrhs, int device) {
+  if (!pattern_ok(sp_a) || nrhs < 1) { fail("ccu_ldl_create: invalid arguments"); return nullptr; }
+  ccu_builder B;
+  const ccu_int n = sp_a[1], nnz = pattern_nnz(sp_a);
+  std::vector<ccu_int> a(nnz), x(n * nrhs);
+  for (ccu_int k = 0; k < nnz; ++k) a[k] = B.b.input(0, k);
+  for (ccu_int i = 0; i < n * nrhs; ++i) x[i] = B.b.input(1, i);
+  ccu_int flag = -1;
+  if (ccu_builder_ldl(&B, sp_a, sp_lt, p, a.data(), x.data(), nrhs, &flag)) return nullptr;
+  return linsol_finish(B, 0, n, nnz, nrhs, x.data(), flag, device);
+}
+
+ccu_linsol* ccu_qr_create(const ccu_int* sp_a, const ccu_int* sp_v, const ccu_int* sp_r, const ccu_int* prinv,
+                          const ccu_int* pc, ccu_int nrhs, int tr, double eps, int device) {
+  if (!pattern_ok(sp_a) || nrhs < 1) { fail("ccu_qr_create: invalid arguments"); return nullptr; }
+  ccu_builder B;
+  const ccu_int n = sp_a[1], nnz = pattern_nnz(sp_a);
+  std::vector<ccu_int> a(nnz), x(n * nrhs);
+  for (ccu_int k = 0; k < nnz; ++k) a[k] = B.b.input(0, k);
+  for (ccu_int i = 0; i < n * nrhs; ++i) x[i] = B.b.input(1, i);
+  ccu_int flag = -1;
+  if (ccu_builder_qr(&B, sp_a, sp_v, sp_r, prinv, pc, a.data(), x.data(), nrhs, tr, eps, &flag)) return nullptr;
+  return linsol_finish(B, 1, n, nnz, nrhs, x.data(), flag, device);
+}
+
+void ccu_linsol_destroy(ccu_linsol* ls) {
+  if (!ls) return;
+  ccu_tape_destroy(ls->tape);
+  delete ls;
+}
+
+ccu_tape* ccu_linsol_tape(ccu_linsol* ls) { return ls ? ls->tape : nullptr; }
+
+int ccu_linsol_solve_host(ccu_linsol* ls, ccu_int N, const double* A, const double* B, double* X, ccu_int* n_flagged) {
+  if (!ls || !A || !B || !X) return fail("ccu_linsol_solve_host: null argument");
+  double flag = 0;
+  const double* arg[2] = {A, B};
+  double* res[2] = {X, &flag};
+  const int reduce_out[2] = {0, 1};
+  if (eval_host_impl(ls->tape, N, arg, res, nullptr, reduce_out)) return 1;
+  if (n_flagged) *n_flagged = static_cast<ccu_int>(flag);
+  return 0;
+}
+
+int ccu_linsol_solve_device(ccu_linsol* ls, ccu_int N, const double* d_A, const double* d_B, double* d_X, double* d_flagged,
+                            int layout, void* stream) {
+  if (!ls || !d_A || !d_B || !d_X) return fail("ccu_linsol_solve_device: null argument");
+  const double* arg[2] = {d_A, d_B};
+  double* res[2] = {d_X, d_flagged};
+  const int reduce_out[2] = {0, 1};
+  return ccu_map_eval_reduce_device(ls->tape, N, arg, res, nullptr, reduce_out, layout, stream);
 }
 
 int ccu_tape_last_kernel_ms(ccu_tape* t, double* ms) {

@@ -155,6 +155,58 @@ CCU_EXPORT int ccu_map_eval_reduce_device(ccu_tape* t, ccu_int N, const double* 
                                           double* const* d_res, const int* reduce_in,
                                           const int* reduce_out, int layout, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Tape builder  --  records scalar operations, and whole runtime algorithms traced over a sparsity pattern
+ * shared by the batch, into the tape format above.  Replaces, for mapped functions, the per-instance calls
+ *   casadi_ldl / casadi_ldl_solve   casadi/core/runtime/casadi_ldl.hpp:25-109  (LinsolLdl::nfact/solve,
+ *                                   casadi/solvers/linsol_ldl.cpp:119-132)
+ *   casadi_qr / casadi_qr_solve /   casadi/core/runtime/casadi_qr.hpp:24-227   (LinsolQr::nfact/solve,
+ *   casadi_qr_singular              casadi/solvers/linsol_qr.cpp:126-180)
+ *   casadi_mtimes                   casadi/core/runtime/casadi_mtimes.hpp:22-75 (Multiplication::eval)
+ * with the same floating-point operations in the same order.  Patterns are the reference's compressed CCS
+ * vectors [nrow, ncol, colind[ncol+1], row[nnz]] (Sparsity::operator const casadi_int*, sparsity.cpp:1734);
+ * values are handles returned by the builder.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ccu_builder ccu_builder;
+CCU_EXPORT ccu_builder* ccu_builder_create(void);
+CCU_EXPORT void ccu_builder_destroy(ccu_builder* b);
+CCU_EXPORT ccu_int ccu_builder_const(ccu_builder* b, double c);                 /* -> handle            */
+CCU_EXPORT ccu_int ccu_builder_input(ccu_builder* b, ccu_int idx, ccu_int nz);  /* -> handle of arg[idx][nz] */
+/* op = enum Operation (calculus.hpp:60-218); y is ignored for unary operations.  -> handle, -1 on error */
+CCU_EXPORT ccu_int ccu_builder_op(ccu_builder* b, int op, ccu_int x, ccu_int y);
+CCU_EXPORT int ccu_builder_output(ccu_builder* b, ccu_int idx, ccu_int nz, ccu_int v); /* res[idx][nz] = v */
+/* a: nnz(A) handles; x: n*nrhs handles, right-hand sides on entry, solutions on return.
+ * zero_pivots (optional): handle of the number of zeros in D (LinsolLdl::nfact warns, linsol_ldl.cpp:122-124). */
+CCU_EXPORT int ccu_builder_ldl(ccu_builder* b, const ccu_int* sp_a, const ccu_int* sp_lt, const ccu_int* p,
+                               const ccu_int* a, ccu_int* x, ccu_int nrhs, ccu_int* zero_pivots);
+/* nullity (optional): handle of the number of |R_cc| < eps (LinsolQr::nfact fails when > 0, linsol_qr.cpp:146-163) */
+CCU_EXPORT int ccu_builder_qr(ccu_builder* b, const ccu_int* sp_a, const ccu_int* sp_v, const ccu_int* sp_r,
+                              const ccu_int* prinv, const ccu_int* pc, const ccu_int* a, ccu_int* x, ccu_int nrhs,
+                              int tr, double eps, ccu_int* nullity);
+/* z += x*y (handles in z are replaced) */
+CCU_EXPORT int ccu_builder_mtimes(ccu_builder* b, const ccu_int* x, const ccu_int* sp_x, const ccu_int* y,
+                                  const ccu_int* sp_y, ccu_int* z, const ccu_int* sp_z);
+/* compile what has been recorded; the builder can be destroyed afterwards */
+CCU_EXPORT ccu_tape* ccu_builder_finish(ccu_builder* b, ccu_int n_in, const ccu_int* nnz_in, ccu_int n_out,
+                                        const ccu_int* nnz_out, int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched linear solves with shared sparsity: factorise and solve N systems A_i x_i = b_i.
+ * A: N x nnz(A) values (AoS, CCS order), B/X: N x (n*nrhs).  n_flagged / d_flagged receive the number of
+ * instances with a zero pivot in D (LDL) or with a numerically singular R (QR, |R_cc| < eps).
+ * ---------------------------------------------------------------------------------------------- */
+CCU_EXPORT ccu_linsol* ccu_ldl_create(const ccu_int* sp_a, const ccu_int* sp_lt, const ccu_int* p, ccu_int nrhs,
+                                      int device);
+CCU_EXPORT ccu_linsol* ccu_qr_create(const ccu_int* sp_a, const ccu_int* sp_v, const ccu_int* sp_r,
+                                     const ccu_int* prinv, const ccu_int* pc, ccu_int nrhs, int tr, double eps,
+                                     int device);
+CCU_EXPORT void ccu_linsol_destroy(ccu_linsol* ls);
+CCU_EXPORT ccu_tape* ccu_linsol_tape(ccu_linsol* ls); /* the traced tape (info, mode, plan); owned by ls */
+CCU_EXPORT int ccu_linsol_solve_host(ccu_linsol* ls, ccu_int N, const double* A, const double* B, double* X,
+                                     ccu_int* n_flagged);
+CCU_EXPORT int ccu_linsol_solve_device(ccu_linsol* ls, ccu_int N, const double* d_A, const double* d_B, double* d_X,
+                                       double* d_flagged, int layout, void* stream);
+
 /* Time (ms) of the most recent kernel launch sequence of this tape, measured with CUDA events on
  * the launching stream (synchronises).  FStats analogue (casadi/core/timing.hpp:47-98). */
 CCU_EXPORT int ccu_tape_last_kernel_ms(ccu_tape* t, double* ms);

@@ -11,6 +11,7 @@
 #include <limits>
 #include <random>
 #include <functional>
+#include <unistd.h>
 #include "models.hpp"
 
 using namespace casadi;
@@ -100,6 +101,15 @@ struct Rng {
 
 int main(int argc, char** argv) {
   g_outdir = argc > 1 ? argv[1] : ".";
+  {  // Linsol plugins live next to libcasadi.so: <exe dir>/../lib
+    char buf[4096];
+    ssize_t len = readlink("/proc/self/exe", buf, sizeof(buf) - 1);
+    if (len > 0) {
+      std::string p(buf, len);
+      p = p.substr(0, p.rfind('/'));
+      GlobalOptions::setCasadiPath(p.substr(0, p.rfind('/')) + "/lib");
+    }
+  }
   using namespace ccu_models;
   const double nan = std::numeric_limits<double>::quiet_NaN(), inf = std::numeric_limits<double>::infinity();
 
@@ -234,6 +244,30 @@ int main(int argc, char** argv) {
       if (j == 1) return sp[i % ns];
       return cs[i % nc];
     }, "opcover_special");
+  }
+  // config 4: KKT systems -- MX function [x = solve(K,b,solver); r = K*x-b] mapped serially, plus the symbolic
+  // factorisation data the Linsol plugins compute in init (linsol_ldl.cpp:67-100, linsol_qr.cpp:67-84)
+  {
+    Sparsity sp = kkt_sparsity();
+    std::vector<casadi_int> p, prinv, pc;
+    Sparsity lt = sp.ldl(p, true);
+    Sparsity spv, spr;
+    sp.qr_sparse(spv, spr, prinv, pc, true);
+    auto dumpv = [&](FILE* fp, const std::vector<casadi_int>& v) { wr64(fp, v.size()); wr(fp, v.data(), 8 * v.size()); };
+    FILE* fp = fopen((g_outdir + "/kkt.sym").c_str(), "wb");
+    wr(fp, "CCUSYM01", 8);
+    dumpv(fp, sp.compress()); dumpv(fp, lt.compress()); dumpv(fp, p);
+    dumpv(fp, spv.compress()); dumpv(fp, spr.compress()); dumpv(fp, prinv); dumpv(fp, pc);
+    fclose(fp);
+    for (std::string solver : {"ldl", "qr"}) {
+      Function f = kkt_solve(solver);
+      const long long N = 150;
+      Rng r(7);
+      dump_case(f, "kkt_" + solver, N, [&](int j, long long i, long long k) {
+        if (j == 0) { static std::vector<double> v; static long long cur = -1; if (cur != i) { v = kkt_values(sp, i); cur = i; } return v[k]; }
+        return r.u(-1, 1);
+      });
+    }
   }
   return 0;
 }

@@ -78,6 +78,15 @@ def main():
                 np.savez_compressed(os.path.join(gold, fn + ".npz"), **read_tape(p))
             elif fn.endswith(".case"):
                 np.savez_compressed(os.path.join(gold, fn + ".npz"), **read_case(p))
+            elif fn.endswith(".sym"):
+                b = open(p, "rb").read()
+                assert b[:8] == b"CCUSYM01"
+                off, arrs = 8, {}
+                for name in ("sp_a", "sp_lt", "p", "sp_v", "sp_r", "prinv", "pc"):
+                    n = int(np.frombuffer(b, dtype=np.int64, count=1, offset=off)[0]); off += 8
+                    arrs[name] = np.frombuffer(b, dtype=np.int64, count=n, offset=off); off += 8 * n
+                assert off == len(b)
+                np.savez_compressed(os.path.join(gold, fn + ".npz"), **arrs)
             elif fn.endswith(".npz"):
                 os.replace(p, os.path.join(gold, fn))
     total = sum(os.path.getsize(os.path.join(gold, f)) for f in os.listdir(gold))

@@ -43,24 +43,17 @@ class IoDesc(ctypes.Structure):
                 ("out", ctypes.c_void_p * 32), ("out_si", ctypes.c_longlong * 32), ("out_sk", ctypes.c_longlong * 32)]
 
 
-def run_generated(tape_name, case_name, seg_instr, nmax=40, null_in=None):
-    os.environ["CCU_JIT_SEG"] = str(seg_instr)
-    try:
-        t = CudaTape(load_tape(tape_name), device=-1)
-        sources = t.jit_sources()
-    finally:
-        del os.environ["CCU_JIT_SEG"]
-    case = load_case(case_name)
-    N = min(case["N"], nmax)
-    ins = [np.ascontiguousarray(a[:N * n]) for a, n in zip(case["in"], t.nnz_in)]
-    outs = [np.full(N * n, np.nan) for n in t.nnz_out]
+def run_sources_on_host(sources, nnz_in, nnz_out, ins, N, null_in=None):
+    """Compile the generated CUDA source of every segment with g++ and run it for N instances (AoS buffers)."""
+    ins = [np.ascontiguousarray(a, np.float64) for a in ins]
+    outs = [np.full(N * n, np.nan) for n in nnz_out]
     io = IoDesc()
     for j, a in enumerate(ins):
         io.in_[j] = None if (a.size == 0 or (null_in is not None and j in null_in)) else a.ctypes.data
-        io.in_si[j], io.in_sk[j] = t.nnz_in[j], 1
+        io.in_si[j], io.in_sk[j] = nnz_in[j], 1
     for j, a in enumerate(outs):
         io.out[j] = a.ctypes.data if a.size else None
-        io.out_si[j], io.out_sk[j] = t.nnz_out[j], 1
+        io.out_si[j], io.out_sk[j] = nnz_out[j], 1
     nslots = max([int(s.split("CCU_ST(")[k].split(",")[0]) for s in sources for k in range(1, len(s.split("CCU_ST(")))
                   if s.split("CCU_ST(")[k][0].isdigit()] + [0]) + 1
     scratch = np.full(nslots * N, np.nan)
@@ -78,6 +71,20 @@ def run_generated(tape_name, case_name, seg_instr, nmax=40, null_in=None):
             lib = ctypes.CDLL(os.path.join(tmp, "seg%d.so" % k))
             lib.run_seg(ctypes.byref(io), ctypes.c_longlong(0), ctypes.c_longlong(N),
                         scratch.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(N))
+    return outs
+
+
+def run_generated(tape_name, case_name, seg_instr, nmax=40, null_in=None):
+    os.environ["CCU_JIT_SEG"] = str(seg_instr)
+    try:
+        t = CudaTape(load_tape(tape_name), device=-1)
+        sources = t.jit_sources()
+    finally:
+        del os.environ["CCU_JIT_SEG"]
+    case = load_case(case_name)
+    N = min(case["N"], nmax)
+    ins = [a[:N * n] for a, n in zip(case["in"], t.nnz_in)]
+    outs = run_sources_on_host(sources, t.nnz_in, t.nnz_out, ins, N, null_in)
     return len(sources), outs, [w[:N * n] for w, n in zip(case["out"], t.nnz_out)]
 
 

@@ -53,3 +53,31 @@ def test_ulp_distance_helper_resolves_single_ulps():
     b = np.array([np.nextafter(1.0, 2.0), 1.193502122111056, np.nextafter(np.nextafter(-3.5, 0), 0), -0.0, np.nan, np.inf])
     d = ulp_diff(a, b)
     assert list(d[:5]) == [1.0, 1.0, 2.0, 0.0, 0.0] and d[5] == np.inf
+
+
+def _kkt():
+    z = np.load(__import__("os").path.join(__import__("casadi_b200.tapeio", fromlist=["GOLDEN_DIR"]).GOLDEN_DIR, "kkt.sym.npz"))
+    return {k: np.array(z[k]) for k in z.files}
+
+
+def dense_sp(nrow, ncol):
+    return np.array([nrow, ncol] + [nrow * c for c in range(ncol + 1)] + [r for _ in range(ncol) for r in range(nrow)],
+                    np.int64)
+
+
+@pytest.mark.parametrize("solver", ["ldl", "qr"])
+def test_oracle_linsol_matches_reference_mx_solve(solver):
+    """oracle_ldl/_solve, oracle_qr/_solve and oracle_mtimes against the reference's own
+    MX function [x = solve(K,b,solver); r = mtimes(K,x)-b] mapped serially over 150 KKT systems."""
+    sym, case = _kkt(), load_case("kkt_" + solver)
+    N, nnz, n = case["N"], int(sym["sp_a"][2 + 60]), 60
+    K, B = case["in"][0].reshape(N, nnz), case["in"][1].reshape(N, n)
+    X, R = case["out"][0].reshape(N, n), case["out"][1].reshape(N, n)
+    for i in range(N):
+        if solver == "ldl":
+            x = oracle.ldl_factor_solve(sym["sp_a"], sym["sp_lt"], sym["p"], K[i], B[i])[0]
+        else:
+            x = oracle.qr_factor_solve(sym["sp_a"], sym["sp_v"], sym["sp_r"], sym["prinv"], sym["pc"], K[i], B[i])[0]
+        assert_bit_equal(x, X[i], "%s x[%d]" % (solver, i))
+        r = oracle.mtimes(K[i], sym["sp_a"], x, dense_sp(n, 1), np.zeros(n), dense_sp(n, 1)) - B[i]
+        assert_bit_equal(r, R[i], "%s r[%d]" % (solver, i))
