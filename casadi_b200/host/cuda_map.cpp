@@ -2,10 +2,15 @@
  * CudaMap -- see cuda_map.hpp.  New file for casadi/core/.
  */
 #include "cuda_map.hpp"
+#include "linsol.hpp"
+#include "mx_node.hpp"
+#include "solve.hpp"
 
 #include <dlfcn.h>
 
 #include <cstdlib>
+#include <cstring>
+#include <map>
 #include <mutex>
 
 namespace casadi {
@@ -22,6 +27,21 @@ namespace casadi {
                            ccu_int, const ccu_int*, ccu_int, const ccu_int*, int) = nullptr;
       void (*tape_destroy)(void*) = nullptr;
       int (*map_eval_host)(void*, ccu_int, const double* const*, double* const*) = nullptr;
+      int (*map_eval_reduce_host)(void*, ccu_int, const double* const*, double* const*, const int*, const int*) = nullptr;
+      // tape builder (MX functions that cannot be expanded are lowered to one scalar tape)
+      void* (*builder_create)() = nullptr;
+      void (*builder_destroy)(void*) = nullptr;
+      ccu_int (*builder_const)(void*, double) = nullptr;
+      ccu_int (*builder_input)(void*, ccu_int, ccu_int) = nullptr;
+      ccu_int (*builder_op)(void*, int, ccu_int, ccu_int) = nullptr;
+      int (*builder_output)(void*, ccu_int, ccu_int, ccu_int) = nullptr;
+      int (*builder_ldl)(void*, const ccu_int*, const ccu_int*, const ccu_int*, const ccu_int*, ccu_int*, ccu_int,
+                         ccu_int*) = nullptr;
+      int (*builder_qr)(void*, const ccu_int*, const ccu_int*, const ccu_int*, const ccu_int*, const ccu_int*,
+                        const ccu_int*, ccu_int*, ccu_int, int, double, ccu_int*) = nullptr;
+      int (*builder_mtimes)(void*, const ccu_int*, const ccu_int*, const ccu_int*, const ccu_int*, ccu_int*,
+                            const ccu_int*) = nullptr;
+      void* (*builder_finish)(void*, ccu_int, const ccu_int*, ccu_int, const ccu_int*, int) = nullptr;
     };
 
     CudaLib& cuda_lib() {
@@ -43,6 +63,18 @@ namespace casadi {
         lib.tape_create = reinterpret_cast<decltype(lib.tape_create)>(sym("ccu_tape_create"));
         lib.tape_destroy = reinterpret_cast<decltype(lib.tape_destroy)>(sym("ccu_tape_destroy"));
         lib.map_eval_host = reinterpret_cast<decltype(lib.map_eval_host)>(sym("ccu_map_eval_host"));
+        lib.map_eval_reduce_host =
+          reinterpret_cast<decltype(lib.map_eval_reduce_host)>(sym("ccu_map_eval_reduce_host"));
+        lib.builder_create = reinterpret_cast<decltype(lib.builder_create)>(sym("ccu_builder_create"));
+        lib.builder_destroy = reinterpret_cast<decltype(lib.builder_destroy)>(sym("ccu_builder_destroy"));
+        lib.builder_const = reinterpret_cast<decltype(lib.builder_const)>(sym("ccu_builder_const"));
+        lib.builder_input = reinterpret_cast<decltype(lib.builder_input)>(sym("ccu_builder_input"));
+        lib.builder_op = reinterpret_cast<decltype(lib.builder_op)>(sym("ccu_builder_op"));
+        lib.builder_output = reinterpret_cast<decltype(lib.builder_output)>(sym("ccu_builder_output"));
+        lib.builder_ldl = reinterpret_cast<decltype(lib.builder_ldl)>(sym("ccu_builder_ldl"));
+        lib.builder_qr = reinterpret_cast<decltype(lib.builder_qr)>(sym("ccu_builder_qr"));
+        lib.builder_mtimes = reinterpret_cast<decltype(lib.builder_mtimes)>(sym("ccu_builder_mtimes"));
+        lib.builder_finish = reinterpret_cast<decltype(lib.builder_finish)>(sym("ccu_builder_finish"));
         if (!ok) {
           lib.error = "'" + name + "' does not export the casadi_cuda.h entry points";
           lib.handle = nullptr;
@@ -53,13 +85,231 @@ namespace casadi {
       });
       return lib;
     }
+
+    // ------------------------------------------------------------------------------------------------
+    // Lowering of an MX function to ONE scalar tape through the tape builder of libcasadi_cuda.so.
+    // Walks the MX algorithm the way MXFunction::eval does (mx_function.cpp:435-490) and the way the
+    // reference's own exporter reads it (mx_function.cpp:1620-1630: instruction_id/_MX/_input/_output),
+    // keeping one value handle per nonzero of every work-vector element; each node is replayed with the
+    // floating-point operations of its numeric eval, Linsol calls by tracing casadi_ldl / casadi_qr over
+    // the (shared) pattern.  Only the vocabulary below is supported; anything else raises.
+    // ------------------------------------------------------------------------------------------------
+    typedef std::vector<ccu_int> Vals;
+
+    struct Lowering {
+      CudaLib& lib;
+      void* b;
+      std::map<unsigned long long, ccu_int> const_cache;
+      ccu_int fail_count = -1;  // sum over QR solves of (nullity != 0)
+
+      explicit Lowering(CudaLib& l) : lib(l), b(l.builder_create()) {}
+
+      ccu_int cst(double v) {
+        unsigned long long bits;
+        std::memcpy(&bits, &v, 8);
+        auto it = const_cache.find(bits);
+        if (it != const_cache.end()) return it->second;
+        ccu_int h = lib.builder_const(b, v);
+        const_cache[bits] = h;
+        return h;
+      }
+      ccu_int op(int o, ccu_int x, ccu_int y = -1) {
+        ccu_int h = lib.builder_op(b, o, x, y);
+        casadi_assert(h >= 0, "Map 'cuda': " + std::string(lib.last_error()));
+        return h;
+      }
+      static std::vector<ccu_int> pattern(const Sparsity& sp) {
+        std::vector<casadi_int> c = sp.compress();
+        return std::vector<ccu_int>(c.begin(), c.end());
+      }
+
+      // Inline an SX function: replay its tape (sx_function.cpp:111-124) over handles
+      void call_sx(const Function& f, const std::vector<const Vals*>& arg, std::vector<Vals*>& res) {
+        std::vector<ccu_int> w(f.sz_w(), -1);
+        casadi_int n = f.n_instructions();
+        for (casadi_int k = 0; k < n; ++k) {
+          casadi_int o = f.instruction_id(k);
+          std::vector<casadi_int> in = f.instruction_input(k), out = f.instruction_output(k);
+          if (o == OP_CONST) {
+            w[out.at(0)] = cst(f.instruction_constant(k));
+          } else if (o == OP_INPUT) {
+            const Vals* a = arg.at(in.at(0));
+            w[out.at(0)] = a ? a->at(in.at(1)) : cst(0.);
+          } else if (o == OP_OUTPUT) {
+            if (res.at(out.at(0))) res[out.at(0)]->at(out.at(1)) = w[in.at(0)];
+          } else {
+            casadi_assert(o != OP_CALL && o != OP_PARAMETER, "Map 'cuda': unsupported SX instruction in '" + f.name() + "'");
+            w[out.at(0)] = op(static_cast<int>(o), w[in.at(0)], in.size() > 1 ? w[in.at(1)] : -1);
+          }
+        }
+      }
+
+      // Lower an MX function given the handles of its arguments; fills res (pre-sized by the caller)
+      void call_mx(const Function& f, const std::vector<const Vals*>& arg, std::vector<Vals*>& res) {
+        std::map<casadi_int, Vals> w;  // work-vector element -> handles
+        casadi_int n = f.n_instructions();
+        for (casadi_int k = 0; k < n; ++k) {
+          casadi_int o = f.instruction_id(k);
+          MX x = f.instruction_MX(k);
+          std::vector<casadi_int> in = f.instruction_input(k), out = f.instruction_output(k);
+          auto W = [&](casadi_int i) -> const Vals& {
+            auto it = w.find(i);
+            casadi_assert(it != w.end(), "Map 'cuda': MX work element read before it is written");
+            return it->second;
+          };
+          if (o == OP_INPUT) {
+            Dict inf = x.info();
+            casadi_int ind = inf.at("ind"), off = inf.at("offset");
+            Vals v(x.nnz());
+            for (casadi_int e = 0; e < x.nnz(); ++e) v[e] = arg.at(ind) ? arg[ind]->at(off + e) : cst(0.);
+            w[out.at(0)] = v;
+          } else if (o == OP_OUTPUT) {
+            Dict inf = x.info();
+            casadi_int ind = inf.at("ind"), off = inf.at("offset");
+            const Vals& v = W(in.at(0));
+            if (res.at(ind)) for (size_t e = 0; e < v.size(); ++e) res[ind]->at(off + e) = v[e];
+          } else if (o == OP_CONST) {
+            DM v = static_cast<DM>(x);
+            Vals r(v.nnz());
+            for (casadi_int e = 0; e < v.nnz(); ++e) r[e] = cst(v.nonzeros()[e]);
+            w[out.at(0)] = r;
+          } else if (o == OP_MTIMES) {
+            casadi_assert(x.class_name() == "Multiplication", "Map 'cuda': " + x.class_name()
+                          + " is not supported on the device (only the sparse casadi_mtimes kernel is)");
+            Vals z = W(in.at(0));
+            const Vals &xx = W(in.at(1)), &yy = W(in.at(2));
+            std::vector<ccu_int> spx = pattern(x.dep(1).sparsity()), spy = pattern(x.dep(2).sparsity()),
+                                 spz = pattern(x.sparsity());
+            casadi_assert(lib.builder_mtimes(b, xx.data(), spx.data(), yy.data(), spy.data(), z.data(), spz.data()) == 0,
+                          "Map 'cuda': " + std::string(lib.last_error()));
+            w[out.at(0)] = z;
+          } else if (o == OP_SOLVE) {
+            bool tr = x.info().at("tr");
+            const Linsol* ls = nullptr;
+            if (auto* n0 = dynamic_cast<const LinsolCall<false>*>(x.get())) ls = &n0->linsol_;
+            if (auto* n1 = dynamic_cast<const LinsolCall<true>*>(x.get())) ls = &n1->linsol_;
+            casadi_assert(ls != nullptr, "Map 'cuda': " + x.class_name() + " is not a Linsol call");
+            Vals xs = W(in.at(0));  // right-hand sides, overwritten by the solutions (solve_impl.hpp:60)
+            const Vals& A = W(in.at(1));
+            const Sparsity& sp = ls->sparsity();
+            casadi_int nrhs = x.dep(0).size2();
+            std::vector<ccu_int> spa = pattern(sp);
+            if (ls->plugin_name() == "ldl") {
+              // symbolic phase as in LinsolLdl::init (linsol_ldl.cpp:67-100, default options)
+              std::vector<casadi_int> p;
+              Sparsity lt = sp.ldl(p, true);
+              std::vector<ccu_int> splt = pattern(lt), pp(p.begin(), p.end());
+              casadi_assert(lib.builder_ldl(b, spa.data(), splt.data(), pp.data(), A.data(), xs.data(), nrhs, nullptr) == 0,
+                            "Map 'cuda': " + std::string(lib.last_error()));
+            } else if (ls->plugin_name() == "qr") {
+              // symbolic phase as in LinsolQr::init (linsol_qr.cpp:67-84, default options, eps = 1e-12)
+              Sparsity spv, spr;
+              std::vector<casadi_int> prinv, pc;
+              sp.qr_sparse(spv, spr, prinv, pc);
+              std::vector<ccu_int> v1 = pattern(spv), r1 = pattern(spr), pi(prinv.begin(), prinv.end()),
+                                   pcc(pc.begin(), pc.end());
+              ccu_int nullity = -1;
+              casadi_assert(lib.builder_qr(b, spa.data(), v1.data(), r1.data(), pi.data(), pcc.data(), A.data(), xs.data(),
+                                           nrhs, tr ? 1 : 0, 1e-12, &nullity) == 0,
+                            "Map 'cuda': " + std::string(lib.last_error()));
+              ccu_int bad = op(OP_NE, nullity, cst(0.));
+              fail_count = fail_count < 0 ? bad : op(OP_ADD, fail_count, bad);
+            } else {
+              casadi_error("Map 'cuda': linear solver plugin '" + ls->plugin_name()
+                           + "' has no device implementation (supported: ldl, qr)");
+            }
+            w[out.at(0)] = xs;
+          } else if (o == OP_CALL) {
+            Function fc = x.which_function();
+            std::vector<const Vals*> a(fc.n_in(), nullptr);
+            for (casadi_int j = 0; j < fc.n_in(); ++j) if (in.at(j) >= 0) a[j] = &W(in[j]);
+            std::vector<Vals> r(fc.n_out());
+            std::vector<Vals*> rp(fc.n_out(), nullptr);
+            for (casadi_int j = 0; j < fc.n_out(); ++j) {
+              if (out.at(j) < 0) continue;
+              r[j].assign(fc.nnz_out(j), cst(0.));
+              rp[j] = &r[j];
+            }
+            call(fc, a, rp);
+            for (casadi_int j = 0; j < fc.n_out(); ++j) if (out[j] >= 0) w[out[j]] = r[j];
+          } else if (o == OP_HORZCAT || o == OP_VERTCAT || o == OP_DIAGCAT) {
+            Vals r;  // Concat::eval_gen: the nonzeros of the arguments one after the other (concat.cpp)
+            for (casadi_int i : in) { const Vals& v = W(i); r.insert(r.end(), v.begin(), v.end()); }
+            w[out.at(0)] = r;
+          } else if (o == OP_HORZSPLIT || o == OP_VERTSPLIT || o == OP_DIAGSPLIT) {
+            std::vector<casadi_int> off = x.info().at("offset");  // Split::eval_gen (split.cpp)
+            const Vals& v = W(in.at(0));
+            casadi_int no = static_cast<casadi_int>(out.size());
+            for (casadi_int j = 0; j < no; ++j) {
+              if (out[j] < 0) continue;
+              casadi_int nz_first = off.at(j), nz_last = off.at(j + 1);
+              w[out[j]] = Vals(v.begin() + nz_first, v.begin() + nz_last);
+            }
+          } else if (o == OP_RESHAPE) {
+            w[out.at(0)] = W(in.at(0));
+          } else if (o == OP_GETNONZEROS) {
+            Dict inf = x.info();
+            casadi_assert(inf.find("nz") != inf.end(), "Map 'cuda': " + x.class_name() + " (sliced GetNonzeros) is not supported");
+            std::vector<casadi_int> nz = inf.at("nz");
+            const Vals& v = W(in.at(0));
+            Vals r(nz.size());
+            for (size_t e = 0; e < nz.size(); ++e) r[e] = nz[e] >= 0 ? v.at(nz[e]) : cst(0.);
+            w[out.at(0)] = r;
+          } else if (o == OP_HORZREPMAT) {
+            const Vals& v = W(in.at(0));  // HorzRepmat::eval_gen (repmat.cpp:44-50)
+            Vals r;
+            casadi_int reps = v.empty() ? 0 : x.nnz() / static_cast<casadi_int>(v.size());
+            for (casadi_int i = 0; i < reps; ++i) r.insert(r.end(), v.begin(), v.end());
+            w[out.at(0)] = r;
+          } else if (o == OP_HORZREPSUM) {
+            const Vals& v = W(in.at(0));  // HorzRepsum::eval_gen (repmat.cpp:127-135): zero, then += in order
+            casadi_int nnz = x.nnz(), reps = nnz ? static_cast<casadi_int>(v.size()) / nnz : 0;
+            Vals r(nnz, cst(0.));
+            for (casadi_int i = 0; i < reps; ++i)
+              for (casadi_int e = 0; e < nnz; ++e) r[e] = op(OP_ADD, r[e], v[i * nnz + e]);
+            w[out.at(0)] = r;
+          } else if (x.n_dep() == 2 && casadi_math<double>::is_binary(static_cast<unsigned char>(o))
+                     && (x.class_name().find("BinaryMX") == 0)) {
+            // BinaryMX<ScX,ScY>::eval_gen (binary_mx.cpp): element-wise, scalars broadcast
+            const Vals &a = W(in.at(0)), &c = W(in.at(1));
+            casadi_int nn = x.nnz();
+            bool sa = a.size() == 1 && nn != 1, sc = c.size() == 1 && nn != 1;
+            casadi_assert((sa || static_cast<casadi_int>(a.size()) == nn) && (sc || static_cast<casadi_int>(c.size()) == nn),
+                          "Map 'cuda': operand patterns of " + x.class_name() + " do not match its result");
+            Vals r(nn);
+            for (casadi_int e = 0; e < nn; ++e) r[e] = op(static_cast<int>(o), a[sa ? 0 : e], c[sc ? 0 : e]);
+            w[out.at(0)] = r;
+          } else if (x.n_dep() == 1 && casadi_math<double>::is_unary(static_cast<unsigned char>(o))
+                     && x.class_name() == "UnaryMX") {
+            const Vals& a = W(in.at(0));
+            Vals r(a.size());
+            for (size_t e = 0; e < a.size(); ++e) r[e] = op(static_cast<int>(o), a[e]);
+            w[out.at(0)] = r;
+          } else {
+            casadi_error("Map 'cuda': MX operation '" + x.class_name() + "' (op " + str(o) + ") in function '" + f.name()
+                         + "' has no device lowering");
+          }
+        }
+      }
+
+      void call(const Function& f, const std::vector<const Vals*>& arg, std::vector<Vals*>& res) {
+        if (f.is_a("SXFunction")) {
+          call_sx(f, arg, res);
+        } else if (f.is_a("MXFunction")) {
+          call_mx(f, arg, res);
+        } else {
+          casadi_error("Map 'cuda': embedded function '" + f.name() + "' of class " + f.class_name()
+                       + " has no device lowering");
+        }
+      }
+    };
   } // namespace
 
   CudaMap::CudaMap(const std::string& name, const Function& f, casadi_int n)
-    : Map(name, f, n), device_(0) {
+    : Map(name, f, n), device_(0), builder_(nullptr), has_flag_(false) {
   }
 
-  CudaMap::CudaMap(DeserializingStream& s) : Map(s), device_(0) {
+  CudaMap::CudaMap(DeserializingStream& s) : Map(s), device_(0), builder_(nullptr), has_flag_(false) {
     // The device program is not serialized (Map::serialize_body packs f_ and n_ only, map.cpp:94-98):
     // it is re-exported from f_, exactly like a freshly created map
     export_function();
@@ -67,6 +317,7 @@ namespace casadi {
 
   CudaMap::~CudaMap() {
     clear_mem();
+    if (builder_) cuda_lib().builder_destroy(builder_);
   }
 
   bool CudaMap::is_a(const std::string& type, bool recursive) const {
@@ -112,21 +363,66 @@ namespace casadi {
   }
 
   void CudaMap::export_function() {
+    builder_ = nullptr;
+    has_flag_ = false;
     if (f_.is_a("SXFunction")) {
       sx_ = f_;
     } else {
       // An MX function whose nodes all have an SX evaluation (mapaccum/fold towers, wrapped maps)
-      // collapses to one SX tape; anything else (e.g. a Linsol call, solve_impl.hpp:57-73) cannot
+      // collapses to one SX tape ...
       try {
         sx_ = f_.expand();
       } catch (std::exception& e) {
-        casadi_error("Map 'cuda': function '" + f_.name() + "' (" + f_.class_name() + ") is not an SX "
-                     "function and cannot be expanded into one: " + std::string(e.what()));
+        // ... anything else (e.g. a Linsol call, solve_impl.hpp:57-73: "eval_sx not defined") is lowered
+        // node by node through the tape builder; unsupported nodes raise from there
+        casadi_assert(f_.is_a("MXFunction"), "Map 'cuda': function '" + f_.name() + "' (" + f_.class_name()
+                      + ") is neither an SX nor an MX function");
+        lower_mx();
+        return;
       }
     }
     casadi_assert(!sx_.has_free(), "Map 'cuda': function '" + f_.name() + "' has free variables "
                   + str(sx_.get_free()) + " and cannot be evaluated");
     tape_ = export_tape(sx_);
+  }
+
+  void CudaMap::lower_mx() {
+    CudaLib& lib = cuda_lib();
+    casadi_assert(lib.handle!=nullptr, "Map 'cuda': " + lib.error);
+    casadi_assert(!f_.has_free(), "Map 'cuda': function '" + f_.name() + "' has free variables "
+                  + str(f_.get_free()) + " and cannot be evaluated");
+    Lowering L(lib);
+    try {
+      std::vector<Vals> in(f_.n_in()), out(f_.n_out());
+      std::vector<const Vals*> a(f_.n_in());
+      std::vector<Vals*> r(f_.n_out());
+      for (casadi_int j=0; j<f_.n_in(); ++j) {
+        in[j].resize(f_.nnz_in(j));
+        for (casadi_int e=0; e<f_.nnz_in(j); ++e) in[j][e] = lib.builder_input(L.b, j, e);
+        a[j] = &in[j];
+      }
+      for (casadi_int j=0; j<f_.n_out(); ++j) {
+        out[j].assign(f_.nnz_out(j), L.cst(0.));
+        r[j] = &out[j];
+      }
+      L.call(f_, a, r);
+      for (casadi_int j=0; j<f_.n_out(); ++j)
+        for (casadi_int e=0; e<f_.nnz_out(j); ++e) lib.builder_output(L.b, j, e, out[j][e]);
+      // instances whose QR factorisation is numerically singular make the reference's map fail
+      // (LinsolQr::nfact returns 1, linsol_qr.cpp:146-163): counted in one extra, summed output
+      if (L.fail_count >= 0) {
+        lib.builder_output(L.b, f_.n_out(), 0, L.fail_count);
+        has_flag_ = true;
+      }
+    } catch (...) {
+      lib.builder_destroy(L.b);
+      throw;
+    }
+    builder_ = L.b;
+    tape_ = Tape();
+    for (casadi_int j=0; j<f_.n_in(); ++j) tape_.nnz_in.push_back(f_.nnz_in(j));
+    for (casadi_int j=0; j<f_.n_out(); ++j) tape_.nnz_out.push_back(f_.nnz_out(j));
+    if (has_flag_) tape_.nnz_out.push_back(1);
   }
 
   void CudaMap::init(const Dict& opts) {
@@ -150,6 +446,10 @@ namespace casadi {
     CudaLib& lib = cuda_lib();
     casadi_assert(lib.handle!=nullptr, "Map 'cuda': " + lib.error);
     const Tape& t = tape_;
+    if (builder_) {
+      m->tape = lib.builder_finish(builder_, static_cast<ccu_int>(t.nnz_in.size()), get_ptr(t.nnz_in),
+                                   static_cast<ccu_int>(t.nnz_out.size()), get_ptr(t.nnz_out), device_);
+    } else
     m->tape = lib.tape_create(static_cast<ccu_int>(t.op.size()), get_ptr(t.op), get_ptr(t.i0),
                               get_ptr(t.i1), get_ptr(t.i2), get_ptr(t.d), t.sz_w,
                               static_cast<ccu_int>(t.nnz_in.size()), get_ptr(t.nnz_in),
@@ -172,8 +472,24 @@ namespace casadi {
     m->fstats.at("cuda").tic();
     // Same contract as Map::eval_gen (map.cpp:141-157): instance i of input j is arg[j]+i*nnz_in(j);
     // null arg[j] reads as zero, null res[j] is not computed
-    int flag = lib.map_eval_host(m->tape, n_, arg, res);
+    int flag;
+    double n_failed = 0;
+    if (has_flag_) {
+      // res has sz_res >= n_out + f_.sz_res() entries (Map::init): the scratch tail takes the flag pointer
+      std::vector<double*> r(res, res + n_out_);
+      r.push_back(&n_failed);
+      std::vector<int> red(n_out_ + 1, 0);
+      red[n_out_] = 1;
+      flag = lib.map_eval_reduce_host(m->tape, n_, arg, get_ptr(r), nullptr, get_ptr(red));
+    } else {
+      flag = lib.map_eval_host(m->tape, n_, arg, res);
+    }
     m->fstats.at("cuda").toc();
+    if (!flag && n_failed > 0) {
+      casadi_warning("Map 'cuda': linear solver factorization failed for " + str(static_cast<casadi_int>(n_failed))
+                     + " of " + str(n_) + " instances of '" + f_.name() + "'");
+      return 1;
+    }
     if (flag) {
       casadi_warning("Map 'cuda' evaluation of '" + f_.name() + "' failed: " + std::string(lib.last_error()));
       return 1;

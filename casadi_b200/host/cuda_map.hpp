@@ -72,7 +72,12 @@ namespace casadi {
     Function sx_;
     Tape tape_;
     int device_;
+    // MX functions that cannot be expanded (e.g. Linsol calls) are lowered node by node through the tape
+    // builder of libcasadi_cuda.so; the recorded program lives in builder_ (one compiled tape per memory)
+    void* builder_;
+    bool has_flag_;  // extra summed output: instances whose linear solver factorization failed
     void export_function();
+    void lower_mx();
   };
 
 } // namespace casadi

@@ -37,6 +37,7 @@ struct Buffers {
 };
 
 // evaluate F through the buffer API (function.cpp:1708-1738) on given inputs
+static int g_expect_flag = 0;
 static std::vector<std::vector<double>> eval(const Function& F, const std::vector<std::vector<double>>& in,
                                              const std::vector<bool>& null_in = {}, const std::vector<bool>& null_out = {}) {
   Buffers b;
@@ -53,7 +54,7 @@ static std::vector<std::vector<double>> eval(const Function& F, const std::vecto
     b.res[j] = (j < (casadi_int)null_out.size() && null_out[j]) ? nullptr : b.out[j].data();
   }
   int flag = F(b.arg.data(), b.res.data(), b.iw.data(), b.w.data(), 0);
-  CHECK(flag == 0, "evaluation of " + F.name() + " returned " + str(flag));
+  CHECK(flag == g_expect_flag, "evaluation of " + F.name() + " returned " + str(flag));
   return b.out;
 }
 
@@ -99,10 +100,16 @@ static void host_side_checks() {
   threw = false;
   try { ff.map(4, "cuda"); } catch (std::exception& e) { threw = std::string(e.what()).find("free variables") != std::string::npos; }
   CHECK(threw, "free variables must be rejected at creation");
-  // an MX function with a Linsol call cannot be expanded: loud failure, no fallback
-  threw = false;
-  try { kkt_solve("ldl").map(4, "cuda"); } catch (std::exception& e) { threw = std::string(e.what()).find("cannot be expanded") != std::string::npos; }
-  CHECK(threw, "non-expandable MX function must be rejected");
+  // an MX function that can neither be expanded (Linsol call) nor lowered node by node
+  // (norm_inf has no device lowering) fails loudly at creation: no fallback
+  {
+    Sparsity sp = kkt_sparsity();
+    MX K = MX::sym("K", sp), b = MX::sym("b", 60);
+    Function g("g", {K, b}, {solve(K, b, "ldl"), norm_inf(b)});
+    threw = false;
+    try { g.map(4, "cuda"); } catch (std::exception& e) { threw = std::string(e.what()).find("no device lowering") != std::string::npos; }
+    CHECK(threw, "MX function with an unsupported node must be rejected");
+  }
 }
 
 static void no_gpu_checks() {
@@ -226,6 +233,43 @@ static void gpu_checks() {
   }
 }
 
+// ---- BASELINE config 5: MX function [x = solve(K,b,solver); r = K*x-b] -- not expandable; CudaMap
+//      lowers it node by node, the Linsol call by tracing casadi_ldl / casadi_qr over the shared pattern
+static void kkt_checks() {
+  using namespace ccu_models;
+  Sparsity sp = kkt_sparsity();
+  for (std::string solver : {"ldl", "qr"}) {
+    Function f = kkt_solve(solver);
+    casadi_int n = 500;
+    Function ref = f.map(n, "serial"), F = f.map(n, "cuda");
+    CHECK(F.class_name() == "CudaMap", F.class_name());
+    std::vector<std::vector<double>> in(2);
+    std::mt19937_64 g(12);
+    for (casadi_int i = 0; i < n; ++i) {
+      std::vector<double> v = kkt_values(sp, i);
+      in[0].insert(in[0].end(), v.begin(), v.end());
+      for (int k = 0; k < 60; ++k) in[1].push_back(-1 + 2 * std::generate_canonical<double, 53>(g));
+    }
+    double rel;
+    CHECK(compare(eval(F, in), eval(ref, in), &rel) == 0, "kkt_" + solver + ": x and r must be bit-identical to the serial map");
+    if (solver == "qr") {
+      // a singular instance makes LinsolQr::nfact fail (linsol_qr.cpp:146-163) and the map return 1
+      for (casadi_int k = 0; k < sp.nnz(); ++k) in[0][7 * sp.nnz() + k] = 0;
+      auto fails = [&](const Function& fn) {
+        int before = g_fail;
+        bool failed = false;
+        g_expect_flag = 1;
+        try { eval(fn, in); failed = g_fail == before; } catch (std::exception&) { failed = true; }
+        g_expect_flag = 0;
+        g_fail = before;
+        return failed;
+      };
+      CHECK(fails(ref), "the serial map must fail on a singular system");
+      CHECK(fails(F), "the cuda map must fail on a singular system like the serial map");
+    }
+  }
+}
+
 int main(int argc, char** argv) {
   bool no_gpu = argc > 1 && std::string(argv[1]) == "--no-gpu";
   {  // Linsol plugins live next to libcasadi.so: <exe dir>/../lib
@@ -239,7 +283,7 @@ int main(int argc, char** argv) {
   }
   try {
     host_side_checks();
-    if (no_gpu) no_gpu_checks(); else gpu_checks();
+    if (no_gpu) no_gpu_checks(); else { gpu_checks(); kkt_checks(); }
   } catch (std::exception& e) {
     printf("FAIL: unexpected exception: %s\n", e.what());
     return 1;
