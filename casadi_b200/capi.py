@@ -43,6 +43,8 @@ SYMBOLS = {
     "ccu_map_eval_device": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, ctypes.c_int, c_vp]),
     "ccu_map_eval_reduce_host": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_i_p, c_i_p]),
     "ccu_map_eval_reduce_device": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_i_p, c_i_p, ctypes.c_int, c_vp]),
+    "ccu_map_eval_shard_device": (ctypes.c_int, [c_vp, c_ll, c_ll, c_ll, c_vp, c_vp, c_i_p, c_i_p, c_vp, ctypes.c_int, c_vp]),
+    "ccu_reduce_tree_device": (ctypes.c_int, [ctypes.c_int, c_vp, c_ll, c_ll, c_vp, c_vp]),
     "ccu_builder_create": (c_vp, []),
     "ccu_builder_destroy": (None, [c_vp]),
     "ccu_builder_const": (c_ll, [c_vp, ctypes.c_double]),

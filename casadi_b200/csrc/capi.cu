@@ -453,19 +453,25 @@ int ccu_map_eval_device(ccu_tape* t, ccu_int N, const double* const* d_arg, doub
   return launch(t, io, N, static_cast<cudaStream_t>(stream));
 }
 
-int ccu_map_eval_reduce_device(ccu_tape* t, ccu_int N, const double* const* d_arg, double* const* d_res,
-                               const int* reduce_in, const int* reduce_out, int layout, void* stream_) {
+// shared by ccu_map_eval_reduce_device (part_out == NULL: block sums + tree into d_res[j]) and
+// ccu_map_eval_shard_device (block sums of the shard written to part_out[j], no tree)
+static int eval_reduce_core(ccu_tape* t, ccu_int N, const double* const* d_arg, double* const* d_res,
+                            const int* reduce_in, const int* reduce_out, int layout, cudaStream_t stream,
+                            double* const* part_out) {
   if (check_eval_args(t, N)) return 1;
   if (layout != CCU_LAYOUT_AOS && layout != CCU_LAYOUT_SOA) return fail("unknown layout %d", layout);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CCU_CUDA(cudaSetDevice(t->device));
   const size_t n_out = t->nnz_out.size();
-  // reduced outputs are first evaluated per instance into a temporary (SoA), then tree-summed
+  auto reduced = [&](size_t j) {
+    return reduce_out && reduce_out[j] && t->nnz_out[j] > 0 && (part_out ? part_out[j] != nullptr : d_res[j] != nullptr);
+  };
+  // reduced outputs are first evaluated per instance into a temporary, then tree-summed
   std::vector<double*> res(n_out);
   for (size_t j = 0; j < n_out; ++j) {
-    res[j] = d_res[j];
-    if (reduce_out && reduce_out[j] && d_res[j] && t->nnz_out[j] > 0) {
-      if (t->d_out[j].ensure(static_cast<size_t>(N) * t->nnz_out[j])) return 1;
+    res[j] = d_res ? d_res[j] : nullptr;
+    if (reduce_out && reduce_out[j]) res[j] = nullptr;
+    if (reduced(j)) {
+      if (t->d_out[j].ensure(static_cast<size_t>(std::max<ccu_int>(N, 1)) * t->nnz_out[j])) return 1;
       res[j] = t->d_out[j].p;
     }
   }
@@ -474,13 +480,53 @@ int ccu_map_eval_reduce_device(ccu_tape* t, ccu_int N, const double* const* d_ar
   if (N > 0 && launch(t, io, N, stream)) return 1;
   const long long nblocks = (N + ccu::kReduceBlock - 1) / ccu::kReduceBlock;
   for (size_t j = 0; j < n_out; ++j) {
-    if (!(reduce_out && reduce_out[j] && d_res[j] && t->nnz_out[j] > 0)) continue;
+    if (!reduced(j)) continue;
     const int nnz = static_cast<int>(t->nnz_out[j]);
-    if (t->d_part[j].ensure(static_cast<size_t>(nblocks > 0 ? nblocks : 1) * nnz)) return 1;
-    CCU_CUDA(ccu::launch_block_sums(res[j], io.out_si[j], io.out_sk[j], N, nnz, t->d_part[j].p, stream));
-    CCU_CUDA(ccu::launch_tree(t->d_part[j].p, nblocks, nnz, d_res[j], stream));
-    g_launches += (N > 0 ? 2 : 1);
+    if (part_out) {
+      CCU_CUDA(ccu::launch_block_sums(res[j], io.out_si[j], io.out_sk[j], N, nnz, part_out[j], stream));
+      g_launches += (N > 0 ? 1 : 0);
+    } else {
+      if (t->d_part[j].ensure(static_cast<size_t>(nblocks > 0 ? nblocks : 1) * nnz)) return 1;
+      CCU_CUDA(ccu::launch_block_sums(res[j], io.out_si[j], io.out_sk[j], N, nnz, t->d_part[j].p, stream));
+      CCU_CUDA(ccu::launch_tree(t->d_part[j].p, nblocks, nnz, d_res[j], stream));
+      g_launches += (N > 0 ? 2 : 1);
+    }
   }
+  return 0;
+}
+
+int ccu_map_eval_reduce_device(ccu_tape* t, ccu_int N, const double* const* d_arg, double* const* d_res,
+                               const int* reduce_in, const int* reduce_out, int layout, void* stream) {
+  return eval_reduce_core(t, N, d_arg, d_res, reduce_in, reduce_out, layout, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int ccu_map_eval_shard_device(ccu_tape* t, ccu_int N_global, ccu_int i0, ccu_int n, const double* const* d_arg,
+                              double* const* d_res, const int* reduce_in, const int* reduce_out, double* const* d_part,
+                              int layout, void* stream) {
+  if (!t) return fail("null tape");
+  if (i0 < 0 || n < 0 || i0 + n > N_global) return fail("shard [%lld, %lld) outside the batch of %lld", i0, i0 + n, N_global);
+  if (n > 0 && i0 % ccu::kReduceBlock != 0) return fail("shard offset %lld is not a multiple of the reduction block %d", i0, ccu::kReduceBlock);
+  const size_t n_out = t->nnz_out.size();
+  std::vector<double*> part(n_out, nullptr);
+  bool any = false;
+  for (size_t j = 0; j < n_out; ++j) {
+    if (reduce_out && reduce_out[j] && d_part && d_part[j]) {
+      part[j] = d_part[j] + (i0 / ccu::kReduceBlock) * t->nnz_out[j];
+      any = true;
+    }
+  }
+  if (!any && !(reduce_in))
+    return ccu_map_eval_device(t, n, d_arg, d_res, layout, stream);
+  return eval_reduce_core(t, n, d_arg, d_res, reduce_in, reduce_out, layout, static_cast<cudaStream_t>(stream),
+                          any ? part.data() : nullptr);
+}
+
+int ccu_reduce_tree_device(int device, double* d_part, ccu_int N_global, ccu_int nnz, double* d_out, void* stream) {
+  if (!d_part || !d_out || N_global < 0 || nnz < 0) return fail("ccu_reduce_tree_device: invalid arguments");
+  CCU_CUDA(cudaSetDevice(device));
+  const long long nblocks = (N_global + ccu::kReduceBlock - 1) / ccu::kReduceBlock;
+  CCU_CUDA(ccu::launch_tree(d_part, nblocks, static_cast<int>(nnz), d_out, static_cast<cudaStream_t>(stream)));
+  g_launches++;
   return 0;
 }
 

@@ -3,6 +3,7 @@
  */
 #include "cuda_map.hpp"
 #include "linsol.hpp"
+#include "multiplication.hpp"
 #include "mx_node.hpp"
 #include "solve.hpp"
 
@@ -174,8 +175,12 @@ namespace casadi {
             for (casadi_int e = 0; e < v.nnz(); ++e) r[e] = cst(v.nonzeros()[e]);
             w[out.at(0)] = r;
           } else if (o == OP_MTIMES) {
-            casadi_assert(x.class_name() == "Multiplication", "Map 'cuda': " + x.class_name()
-                          + " is not supported on the device (only the sparse casadi_mtimes kernel is)");
+            // Multiplication::eval_kernel = casadi_mtimes (multiplication.cpp:64-67); the dense variants call BLAS
+            casadi_assert(dynamic_cast<const DenseMultiplication*>(x.get()) == nullptr
+                          && dynamic_cast<const PseudoDenseMultiplication*>(x.get()) == nullptr
+                          && dynamic_cast<const DenseSparseMultiplication*>(x.get()) == nullptr,
+                          "Map 'cuda': dense matrix products (" + x.class_name() + ") are not supported on the "
+                          "device (only the sparse casadi_mtimes kernel is)");
             Vals z = W(in.at(0));
             const Vals &xx = W(in.at(1)), &yy = W(in.at(2));
             std::vector<ccu_int> spx = pattern(x.dep(1).sparsity()), spy = pattern(x.dep(2).sparsity()),
@@ -268,8 +273,7 @@ namespace casadi {
             for (casadi_int i = 0; i < reps; ++i)
               for (casadi_int e = 0; e < nnz; ++e) r[e] = op(OP_ADD, r[e], v[i * nnz + e]);
             w[out.at(0)] = r;
-          } else if (x.n_dep() == 2 && casadi_math<double>::is_binary(static_cast<unsigned char>(o))
-                     && (x.class_name().find("BinaryMX") == 0)) {
+          } else if (x.n_dep() == 2 && x.is_binary()) {
             // BinaryMX<ScX,ScY>::eval_gen (binary_mx.cpp): element-wise, scalars broadcast
             const Vals &a = W(in.at(0)), &c = W(in.at(1));
             casadi_int nn = x.nnz();
@@ -279,8 +283,7 @@ namespace casadi {
             Vals r(nn);
             for (casadi_int e = 0; e < nn; ++e) r[e] = op(static_cast<int>(o), a[sa ? 0 : e], c[sc ? 0 : e]);
             w[out.at(0)] = r;
-          } else if (x.n_dep() == 1 && casadi_math<double>::is_unary(static_cast<unsigned char>(o))
-                     && x.class_name() == "UnaryMX") {
+          } else if (x.n_dep() == 1 && x.is_unary()) {
             const Vals& a = W(in.at(0));
             Vals r(a.size());
             for (size_t e = 0; e < a.size(); ++e) r[e] = op(static_cast<int>(o), a[e]);

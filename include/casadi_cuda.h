@@ -155,6 +155,20 @@ CCU_EXPORT int ccu_map_eval_reduce_device(ccu_tape* t, ccu_int N, const double* 
                                           double* const* d_res, const int* reduce_in,
                                           const int* reduce_out, int layout, void* stream);
 
+/* Multi-GPU: the instances [i0, i0+n) of a batch of N_global are evaluated by this tape's device (instances are
+ * independent, map.cpp:147-155: contiguous shards, no exchange).  d_arg / d_res point at the SHARD's data (its
+ * first instance at index 0; SoA leading dimension n).  For reduce_out outputs the level-0 sums of the shard's
+ * 1024-instance blocks are written at their GLOBAL block positions into d_part[j], a device vector of
+ * ceil(N_global/1024)*nnz_out[j] doubles that the caller zero-initialises; i0 must be a multiple of 1024.
+ * Summing d_part over the ranks (disjoint supports: the sum is exact -- one NCCL all-reduce) and then calling
+ * ccu_reduce_tree_device gives a result that is bit-identical for every number of GPUs, and to
+ * ccu_map_eval_reduce_device on one GPU.  d_part is overwritten by ccu_reduce_tree_device. */
+CCU_EXPORT int ccu_map_eval_shard_device(ccu_tape* t, ccu_int N_global, ccu_int i0, ccu_int n,
+                                         const double* const* d_arg, double* const* d_res, const int* reduce_in,
+                                         const int* reduce_out, double* const* d_part, int layout, void* stream);
+CCU_EXPORT int ccu_reduce_tree_device(int device, double* d_part, ccu_int N_global, ccu_int nnz, double* d_out,
+                                      void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Tape builder  --  records scalar operations, and whole runtime algorithms traced over a sparsity pattern
  * shared by the batch, into the tape format above.  Replaces, for mapped functions, the per-instance calls
