@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--n", type=int, default=10_000_000, help="instances per GPU per step")
+    ap.add_argument("--instances", dest="n", type=int, default=10_000_000, help="instances per GPU per step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-interp", action="store_true")

@@ -99,7 +99,8 @@ struct ccu_tape {
   ccu::Program prog;
   ccu::LaunchPlan plan;
   bool use_acc = true;
-  uint64_t* d_prog = nullptr;
+  ccu::XInstr* d_prog = nullptr;
+  long long n_records = 0;
   DevBuf scratch;
   // staging for the host-pointer path
   std::vector<DevBuf> d_in, d_out, d_part;
@@ -131,37 +132,35 @@ namespace {
 int build_plan(ccu_tape* t, int threads, int ipt, int slots_shared) {
   ccu::CompileOptions opt;
   opt.use_acc = t->use_acc;
-  // automatic choice: keep the whole work vector in shared memory when it is small; otherwise a
-  // fixed shared window and SPILL/FILL to the global scratch
-  if (slots_shared <= 0) slots_shared = t->max_live + 1 <= 96 ? static_cast<int>(t->max_live + 1) : 48;
+  // automatic choice (B200 sweeps, profiles/r1_sweep_interp_v2.jsonl): keep the whole work vector in shared
+  // memory when it is small; otherwise a SMALL shared window (occupancy beats fewer spills: 16 slots x 2 lanes
+  // outran 48 x 1 by 1.9x on the quadrotor tape) and SPILL/FILL to the global scratch
+  const bool fits = t->max_live + 1 <= 32;
+  if (slots_shared <= 0) slots_shared = fits ? static_cast<int>(t->max_live + 1) : 16;
   if (slots_shared < 4) slots_shared = 4;
   opt.slots_shared = slots_shared;
   std::string err;
   ccu::Program prog;
   if (!ccu::compile_tape(t->source(), opt, &prog, &err)) return fail("tape compile failed: %s", err.c_str());
-  if (threads <= 0) threads = 128;
-  if (ipt <= 0) {
-    // two lanes per thread when that still leaves >= 4 CTAs per SM worth of shared memory
-    size_t per_lane = static_cast<size_t>(prog.slots_shared) * 8;
-    ipt = (per_lane * threads * 2 * 4 <= 200 * 1024) ? 2 : 1;
-  }
+  if (threads <= 0) threads = fits ? 256 : 128;
+  if (ipt <= 0) ipt = 2;  // two lanes per thread amortise the dispatch and give the FP64 pipe independent work
   if (threads % 32 != 0 || threads > 1024) return fail("plan: threads must be a multiple of 32, <= 1024");
   if (ipt != 1 && ipt != 2 && ipt != 4) return fail("plan: ipt must be 1, 2 or 4");
+  if (ipt == 4 && threads > 512) return fail("plan: at most 512 threads with 4 instances per thread");
   ccu::LaunchPlan plan;
   plan.threads = threads; plan.ipt = ipt;
   plan.slots_shared = prog.slots_shared; plan.slots_global = prog.slots_global;
-  plan.smem_bytes = static_cast<size_t>(plan.slots_shared) * ipt * threads * sizeof(double);
+  plan.smem_bytes = ccu::plan_smem_bytes(plan);
   if (plan.smem_bytes > 227 * 1024) return fail("plan needs %zu bytes of shared memory per CTA (> 227 KB)", plan.smem_bytes);
   if (t->device >= 0) {
     CCU_CUDA(cudaSetDevice(t->device));
     cudaError_t e = ccu::plan_occupancy(&plan, t->device);
     if (e != cudaSuccess) return fail("plan_occupancy: %s", cudaGetErrorString(e));
     if (t->d_prog) { cudaFree(t->d_prog); t->d_prog = nullptr; }
-    std::vector<uint64_t> padded(prog.words);
-    padded.push_back(ccu::enc(ccu::D_END, 0, 0, 0));
-    padded.push_back(ccu::enc(ccu::D_END, 0, 0, 0));
-    CCU_CUDA(cudaMalloc(&t->d_prog, padded.size() * 8));
-    CCU_CUDA(cudaMemcpy(t->d_prog, padded.data(), padded.size() * 8, cudaMemcpyHostToDevice));
+    std::vector<ccu::XInstr> rec = ccu::predecode(prog.words, threads * ipt);
+    CCU_CUDA(cudaMalloc(&t->d_prog, rec.size() * sizeof(ccu::XInstr)));
+    CCU_CUDA(cudaMemcpy(t->d_prog, rec.data(), rec.size() * sizeof(ccu::XInstr), cudaMemcpyHostToDevice));
+    t->n_records = static_cast<long long>(rec.size());
   }
   t->prog = std::move(prog);
   t->plan = plan;
@@ -189,7 +188,7 @@ int launch(ccu_tape* t, const ccu::IoDesc& io, long long N, cudaStream_t stream)
   }
   if (ensure_scratch(t)) return 1;
   if (t->ev0) cudaEventRecord(t->ev0, stream);
-  cudaError_t e = ccu::launch_interp(t->plan, t->d_prog, io, N, t->scratch.p, stream);
+  cudaError_t e = ccu::launch_interp(t->plan, t->d_prog, t->n_records, io, N, t->scratch.p, stream);
   if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
   if (t->ev1) cudaEventRecord(t->ev1, stream);
   t->timed = true;

@@ -1,7 +1,7 @@
 """BASELINE config 4: mapaccum (T=100) Monte-Carlo rollouts with reduce_out sums across the GPUs of one node.
 
-  python tools/bench_mc.py --n 16777216                                  (1 GPU)
-  python -m torch.distributed.run --nproc-per-node G ... tools/bench_mc.py --n ...   (G GPUs, NCCL all-reduce of block sums)
+  python tools/bench_mc.py --samples 16777216                                  (1 GPU)
+  python -m torch.distributed.run --nproc-per-node G ... tools/bench_mc.py --samples ...   (G GPUs, NCCL all-reduce of block sums)
 
 Inputs are a deterministic function of the GLOBAL instance index, so every world size evaluates the same batch and
 the printed sums must be bit-identical for 1/2/4/8 GPUs (fixed-shape tree, casadi_b200/csrc/reduce.cu)."""
@@ -21,7 +21,7 @@ from casadi_b200.dist import ShardedCudaMap  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=1 << 24, help="total Monte-Carlo samples over all GPUs")
+    ap.add_argument("--samples", dest="n", type=int, default=1 << 24, help="total Monte-Carlo samples over all GPUs")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args()
