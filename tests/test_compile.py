@@ -41,8 +41,15 @@ def emulate(tape_name, case_name, S, nmax=64):
 
 @pytest.mark.parametrize("name", ["cartpole", "cartpole1", "quad1", "mcstep", "mapnode", "opcover"])
 def test_compiled_program_small_tapes_no_spill(name):
-    info = emulate(name, name, 0)
+    info = emulate(name, name, 64)  # every work vector here has at most 58 live values
     assert info["slots_global"] == 0
+
+
+def test_automatic_plan_small_window_for_large_work_vectors():
+    # the automatic plan keeps <= 32 live values entirely in shared memory and otherwise uses a 16-slot window
+    assert emulate("cartpole", "cartpole", 0)["slots_global"] == 0
+    info = emulate("quad1", "quad1", 0)
+    assert info["slots_shared"] == 16 and info["slots_global"] > 0
 
 
 @pytest.mark.parametrize("name,S", [("cartpole", 4), ("cartpole", 8), ("cartpole", 16), ("quad1", 6), ("quad1", 24),
