@@ -115,6 +115,8 @@ struct ccu_tape {
   ccu::JitProgram jit;
   bool jit_built = false;
   std::string jit_error;
+  mutable std::vector<std::string> jit_src;  // ccu_tape_get_jit_source: sources of the option set jit_src_key
+  mutable std::string jit_src_key;
   int sms = 0;
 
   ccu::TapeSource source() const {
@@ -198,6 +200,7 @@ int launch(ccu_tape* t, const ccu::IoDesc& io, long long N, cudaStream_t stream)
 
 void jit_options_from_env(ccu::JitOptions* o) {
   if (const char* p = getenv("CCU_JIT_SEG")) o->seg_instr = atoi(p);
+  if (const char* p = getenv("CCU_JIT_SCHED")) o->schedule = atoi(p);
   if (const char* p = getenv("CCU_JIT_THREADS")) o->threads = atoi(p);
   if (const char* p = getenv("CCU_JIT_MINBLOCKS")) o->min_blocks = atoi(p);
   if (const char* p = getenv("CCU_JIT_BATCH")) o->load_batch = atoi(p);
@@ -381,6 +384,8 @@ int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info) {
     info->jit_max_regs = t->jit.max_regs;
     info->jit_cache_hits = t->jit.cache_hits;
     info->jit_threads = t->jit.threads;
+    info->jit_schedule = t->jit_opt.schedule;
+    info->jit_schedule_ms = static_cast<ccu_int>(t->jit.schedule_ms);
   }
   return 0;
 }
@@ -413,11 +418,40 @@ int ccu_tape_set_jit_plan(ccu_tape* t, int seg_instr, int threads, int min_block
   return 0;
 }
 
+int ccu_tape_jit_plan_stats(const ccu_tape* t, int seg_instr, int schedule, ccu_int stats[8]) {
+  if (!t || !stats) return fail("null argument");
+  ccu::JitOptions o = t->jit_opt;
+  if (seg_instr > 0) o.seg_instr = seg_instr;
+  if (schedule >= 0) o.schedule = schedule;
+  ccu::JitPlanStats ps;
+  std::string err;
+  if (!ccu::jit_plan_stats(t->source(), o, &ps, &err)) return fail("%s", err.c_str());
+  stats[0] = ps.segments; stats[1] = ps.scratch_slots; stats[2] = ps.cross_loads; stats[3] = ps.cross_stores;
+  stats[4] = ps.max_segment; stats[5] = static_cast<ccu_int>(ps.schedule_ms); stats[6] = 0; stats[7] = 0;
+  return 0;
+}
+
+int ccu_tape_set_jit_schedule(ccu_tape* t, int schedule) {
+  if (!t) return fail("null tape");
+  if (schedule < 0 || schedule > 1) return fail("unknown schedule %d", schedule);
+  t->jit_opt.schedule = schedule;
+  return 0;
+}
+
 ccu_int ccu_tape_get_jit_source(const ccu_tape* t, ccu_int segment, char* buf, ccu_int cap) {
   if (!t) { fail("null tape"); return -1; }
-  std::vector<std::string> src;
-  std::string err;
-  if (!ccu::jit_generate(t->source(), t->jit_opt, &src, nullptr, &err)) { fail("%s", err.c_str()); return -1; }
+  // generating re-plans the whole tape: keep the sources of the last option set
+  char key[160];
+  snprintf(key, sizeof key, "%d,%d,%d,%d,%d", t->jit_opt.seg_instr, t->jit_opt.schedule, t->jit_opt.threads,
+           t->jit_opt.min_blocks, t->jit_opt.load_batch);
+  if (t->jit_src_key != key) {
+    std::string err;
+    t->jit_src.clear();
+    t->jit_src_key.clear();
+    if (!ccu::jit_generate(t->source(), t->jit_opt, &t->jit_src, nullptr, &err)) { fail("%s", err.c_str()); return -1; }
+    t->jit_src_key = key;
+  }
+  const std::vector<std::string>& src = t->jit_src;
   if (segment < 0) return static_cast<ccu_int>(src.size());
   if (segment >= static_cast<ccu_int>(src.size())) { fail("segment out of range"); return -1; }
   const std::string& s = src[segment];

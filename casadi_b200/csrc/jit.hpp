@@ -22,11 +22,13 @@
 
 #include "interp.cuh"
 #include "tape_compile.hpp"
+#include "tape_schedule.hpp"
 
 namespace ccu {
 
 struct JitOptions {
   int seg_instr = 800;    // arithmetic instructions per segment
+  int schedule = 1;       // 0 = reference order, fixed-length segments; 1 = min-cut bisection (tape_schedule.hpp)
   int threads = 256;      // CTA size
   int min_blocks = 2;     // __launch_bounds__ second argument: 2 CTAs of 256 threads per SM = at most 128 registers (0 = up to 255)
   int load_batch = 8;     // cross-segment live-ins are loaded in groups of this many (memory-level parallelism)
@@ -46,6 +48,7 @@ struct JitProgram {
   int max_regs = 0;             // max registers per thread over the segments
   int cache_hits = 0;
   double compile_ms = 0;
+  double schedule_ms = 0;       // time spent ordering / cutting the tape (tape_schedule.hpp)
 };
 
 // true when libnvrtc can be loaded in this process
@@ -57,6 +60,13 @@ bool jit_build(const TapeSource& src, const JitOptions& opt, int device, JitProg
 // generated CUDA source of every segment (inspection / tests; no GPU or NVRTC needed)
 bool jit_generate(const TapeSource& src, const JitOptions& opt, std::vector<std::string>* sources,
                   JitProgram* plan, std::string* err);
+
+// the plan alone (host only): segments, scratch slots and traffic for the given options
+struct JitPlanStats {
+  long long segments = 0, scratch_slots = 0, cross_loads = 0, cross_stores = 0, max_segment = 0;
+  double schedule_ms = 0;
+};
+bool jit_plan_stats(const TapeSource& src, const JitOptions& opt, JitPlanStats* out, std::string* err);
 
 // tile size actually used for a batch of N
 long long jit_tile_for(const JitProgram& p, long long N, int sms);

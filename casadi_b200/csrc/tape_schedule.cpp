@@ -1,0 +1,386 @@
+// Min-cut recursive bisection of the tape's value graph.  See tape_schedule.hpp.
+#include "tape_schedule.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdint>
+#include <cstdlib>
+#include <set>
+#include <utility>
+
+namespace ccu {
+namespace {
+
+constexpr int kInf = 1 << 28;
+
+// Dinic's maximum flow on a forward-star graph; blocking flows are found iteratively (dependency chains make
+// augmenting paths thousands of edges long).
+struct FlowNet {
+  struct Edge { int to, cap; };
+  std::vector<Edge> e;
+  std::vector<int> head, nxt, level, it, queue, path;
+  int n = 0;
+
+  void reset(int nodes) {
+    n = nodes;
+    head.assign(n, -1);
+    e.clear();
+    nxt.clear();
+  }
+  int add_node() { head.push_back(-1); return n++; }
+  void add(int a, int b, int c) {
+    e.push_back({b, c}); nxt.push_back(head[a]); head[a] = static_cast<int>(e.size()) - 1;
+    e.push_back({a, 0}); nxt.push_back(head[b]); head[b] = static_cast<int>(e.size()) - 1;
+  }
+  bool bfs(int s, int t) {
+    level.assign(n, -1);
+    queue.clear();
+    queue.push_back(s);
+    level[s] = 0;
+    for (size_t q = 0; q < queue.size(); ++q) {
+      const int u = queue[q];
+      for (int ei = head[u]; ei != -1; ei = nxt[ei])
+        if (e[ei].cap > 0 && level[e[ei].to] < 0) { level[e[ei].to] = level[u] + 1; queue.push_back(e[ei].to); }
+    }
+    return level[t] >= 0;
+  }
+  long long maxflow(int s, int t) {
+    long long flow = 0;
+    while (bfs(s, t)) {
+      it = head;
+      path.clear();
+      int u = s;
+      for (;;) {
+        if (u == t) {
+          int f = kInf;
+          for (int ei : path) f = std::min(f, e[ei].cap);
+          for (int ei : path) { e[ei].cap -= f; e[ei ^ 1].cap += f; }
+          flow += f;
+          size_t k = 0;
+          while (e[path[k]].cap > 0) ++k;  // first saturated edge
+          path.resize(k);
+          u = k ? e[path[k - 1]].to : s;
+          continue;
+        }
+        bool advanced = false;
+        for (int& ei = it[u]; ei != -1; ei = nxt[ei]) {
+          if (e[ei].cap > 0 && level[e[ei].to] == level[u] + 1) {
+            path.push_back(ei);
+            u = e[ei].to;
+            advanced = true;
+            break;
+          }
+        }
+        if (advanced) continue;
+        level[u] = -1;  // dead end
+        if (path.empty()) break;
+        const int ei = path.back();
+        path.pop_back();
+        u = e[ei ^ 1].to;
+        it[u] = nxt[ei];
+      }
+    }
+    return flow;
+  }
+  // nodes reachable from s in the residual graph
+  void reach_from(int s, std::vector<char>* mark) {
+    mark->assign(n, 0);
+    queue.clear();
+    queue.push_back(s);
+    (*mark)[s] = 1;
+    for (size_t q = 0; q < queue.size(); ++q) {
+      const int u = queue[q];
+      for (int ei = head[u]; ei != -1; ei = nxt[ei])
+        if (e[ei].cap > 0 && !(*mark)[e[ei].to]) { (*mark)[e[ei].to] = 1; queue.push_back(e[ei].to); }
+    }
+  }
+  // nodes that can reach t in the residual graph
+  void reach_to(int t, std::vector<char>* mark) {
+    mark->assign(n, 0);
+    queue.clear();
+    queue.push_back(t);
+    (*mark)[t] = 1;
+    for (size_t q = 0; q < queue.size(); ++q) {
+      const int u = queue[q];
+      for (int ei = head[u]; ei != -1; ei = nxt[ei])
+        if (e[ei ^ 1].cap > 0 && !(*mark)[e[ei].to]) { (*mark)[e[ei].to] = 1; queue.push_back(e[ei].to); }
+    }
+  }
+};
+
+struct Bisector {
+  const std::vector<Node>& N;
+  const ScheduleOptions& opt;
+  int n;
+  std::vector<int> cstart, cons;  // distinct consumers of every arithmetic value
+  std::vector<int> loc;           // node -> index in the current piece (-1 = outside)
+  std::vector<char> done;         // node already placed (belongs to an earlier piece)
+  std::vector<int> ext_z;         // external value -> flow node of the current network (-1 = none, -2 = constant)
+  std::vector<int> ext_touched;
+  std::vector<int> out;           // items in final order
+  std::vector<int> seg_starts;    // indices into `out`
+  FlowNet net;
+  long long cuts = 0;
+
+  Bisector(const std::vector<Node>& nodes, const ScheduleOptions& o) : N(nodes), opt(o), n(static_cast<int>(nodes.size())) {
+    std::vector<int> cnt(n + 1, 0);
+    auto each_operand = [&](int k, auto&& f) {
+      const Node& nd = N[k];
+      if (nd.a >= 0 && N[nd.a].kind == K_ARITH) f(nd.a);
+      if (nd.b >= 0 && nd.b != nd.a && N[nd.b].kind == K_ARITH) f(nd.b);
+    };
+    for (int k = 0; k < n; ++k) each_operand(k, [&](int u) { cnt[u + 1]++; });
+    cstart.assign(n + 1, 0);
+    for (int k = 0; k < n; ++k) cstart[k + 1] = cstart[k] + cnt[k + 1];
+    cons.resize(cstart[n]);
+    std::vector<int> fill(cstart.begin(), cstart.end() - 1);
+    for (int k = 0; k < n; ++k) each_operand(k, [&](int u) { cons[fill[u]++] = k; });
+    loc.assign(n, -1);
+    done.assign(n, 0);
+    ext_z.assign(n, -1);
+  }
+
+  template <class F>
+  void operands(int k, F&& f) const {
+    const Node& nd = N[k];
+    if (nd.a >= 0 && N[nd.a].kind == K_ARITH) f(nd.a);
+    if (nd.b >= 0 && nd.b != nd.a && N[nd.b].kind == K_ARITH) f(nd.b);
+  }
+
+  // minimum cut of `piece` with the first/last npin items of `order` pinned; inD[i] for piece index i.
+  // Of the two extreme minimum cuts (smallest / largest D) the more balanced one is returned.
+  long long mincut(const std::vector<int>& piece, const std::vector<int>& order, int npin, std::vector<char>* inD) {
+    const int m = static_cast<int>(piece.size());
+    const int S = 0, T = 1;
+    net.reset(2 + m);
+    auto X = [](int i) { return 2 + i; };
+    for (int j = 0; j < npin; ++j) net.add(S, X(loc[order[j]]), kInf);
+    for (int j = m - npin; j < m; ++j) net.add(X(loc[order[j]]), T, kInf);
+    ext_touched.clear();
+    for (int i = 0; i < m; ++i) {
+      const int v = piece[i];
+      operands(v, [&](int u) {
+        if (loc[u] >= 0) {
+          net.add(X(i), X(loc[u]), kInf);  // closure: v in D => u in D
+          return;
+        }
+        // value of an earlier piece: it stays live across this cut iff one of its readers is outside D.  When it
+        // is also read after this piece it is live whatever the cut.
+        if (ext_z[u] == -1) {
+          bool later = false;
+          for (int q = cstart[u]; q < cstart[u + 1]; ++q) {
+            const int c = cons[q];
+            if (loc[c] < 0 && !done[c]) { later = true; break; }
+          }
+          ext_touched.push_back(u);
+          if (later) {
+            ext_z[u] = -2;
+          } else {
+            ext_z[u] = net.add_node();
+            net.add(S, ext_z[u], 1);
+          }
+        }
+        if (ext_z[u] >= 0) net.add(ext_z[u], X(i), kInf);
+      });
+      if (N[v].kind != K_ARITH) continue;
+      const int nc = cstart[v + 1] - cstart[v];
+      if (nc == 0) continue;
+      bool outside = false;
+      for (int q = cstart[v]; q < cstart[v + 1]; ++q)
+        if (loc[cons[q]] < 0) { outside = true; break; }
+      if (outside) {
+        net.add(X(i), T, 1);  // read after this piece: live across the cut iff v is in D
+      } else if (nc == 1) {
+        net.add(X(i), X(loc[cons[cstart[v]]]), 1);
+      } else {
+        const int z = net.add_node();
+        net.add(X(i), z, 1);
+        for (int q = cstart[v]; q < cstart[v + 1]; ++q) net.add(z, X(loc[cons[q]]), kInf);
+      }
+    }
+    for (int u : ext_touched) ext_z[u] = -1;
+    const long long f = net.maxflow(S, T);
+    ++cuts;
+    std::vector<char> a, b;
+    net.reach_from(S, &a);
+    net.reach_to(T, &b);
+    int na = 0, nb = 0;
+    for (int i = 0; i < m; ++i) { na += a[X(i)]; nb += !b[X(i)]; }
+    inD->assign(m, 0);
+    const bool use_small = std::abs(2 * na - m) <= std::abs(2 * nb - m);
+    for (int i = 0; i < m; ++i) (*inD)[i] = use_small ? a[X(i)] : !b[X(i)];
+    return f;
+  }
+
+  int arith_count(const std::vector<int>& piece) const {
+    int c = 0;
+    for (int v : piece) c += N[v].kind == K_ARITH;
+    return c;
+  }
+
+  void emit(const std::vector<int>& piece) {
+    for (int v : piece) { out.push_back(v); done[v] = 1; }
+  }
+
+  void split(std::vector<int>& piece, bool in_seg) {
+    const int m = static_cast<int>(piece.size());
+    if (!in_seg && arith_count(piece) <= opt.seg_instr) {
+      seg_starts.push_back(static_cast<int>(out.size()));
+      in_seg = true;
+    }
+    if (m <= 2 || (in_seg && m <= std::max(opt.min_piece, 4))) {
+      if (!in_seg) seg_starts.push_back(static_cast<int>(out.size()));
+      emit(piece);
+      return;
+    }
+    for (int i = 0; i < m; ++i) loc[piece[i]] = i;
+    const int npin = std::max(1, std::min(m / 2, static_cast<int>(opt.pin_frac * m)));
+    // order 1: as inherited; order 2: ASAP levels inside the piece
+    std::vector<int> lev(m, 0);
+    int maxlev = 0;
+    for (int i = 0; i < m; ++i) {
+      int l = 0;
+      operands(piece[i], [&](int u) { if (loc[u] >= 0) l = std::max(l, lev[loc[u]] + 1); });
+      lev[i] = l;
+      maxlev = std::max(maxlev, l);
+    }
+    std::vector<int> bucket(maxlev + 2, 0);
+    for (int i = 0; i < m; ++i) bucket[lev[i] + 1]++;
+    for (int l = 0; l <= maxlev; ++l) bucket[l + 1] += bucket[l];
+    std::vector<int> by_level(m);
+    for (int i = 0; i < m; ++i) by_level[bucket[lev[i]]++] = piece[i];
+    std::vector<char> d1, d2;
+    const long long c1 = mincut(piece, piece, npin, &d1);
+    long long c2 = kInf;
+    if (maxlev > 0) c2 = mincut(piece, by_level, npin, &d2);
+    auto imbalance = [&](const std::vector<char>& d) {
+      int k = 0;
+      for (char x : d) k += x;
+      return std::abs(2 * k - m);
+    };
+    const bool second = c2 < c1 || (c2 == c1 && imbalance(d2) < imbalance(d1));
+    const std::vector<char>& d = second ? d2 : d1;
+    for (int i = 0; i < m; ++i) loc[piece[i]] = -1;
+    std::vector<int> A, B;
+    for (int i = 0; i < m; ++i) (d[i] ? A : B).push_back(piece[i]);
+    std::vector<int>().swap(piece);
+    if (A.empty() || B.empty()) {  // cannot happen with pins on both sides; keep the order rather than loop
+      std::vector<int>& all = A.empty() ? B : A;
+      if (!in_seg) seg_starts.push_back(static_cast<int>(out.size()));
+      emit(all);
+      return;
+    }
+    split(A, in_seg);
+    split(B, in_seg);
+  }
+};
+
+}  // namespace
+
+bool schedule_tape(const std::vector<Node>& nodes, const ScheduleOptions& opt, Schedule* S, std::string* err) {
+  const auto t0 = std::chrono::steady_clock::now();
+  const int n = static_cast<int>(nodes.size());
+  *S = Schedule();
+  const int per = std::max(opt.seg_instr, 16);
+  if (opt.method == 0 || n == 0) {
+    S->order.resize(n);
+    for (int k = 0; k < n; ++k) S->order[k] = k;
+    S->seg_begin.push_back(0);
+    int cnt = 0;
+    for (int k = 0; k < n; ++k)
+      if (nodes[k].kind == K_ARITH && ++cnt >= per && k + 1 < n) { cnt = 0; S->seg_begin.push_back(k + 1); }
+    S->seg_begin.push_back(n);
+    return true;
+  }
+  ScheduleOptions o = opt;
+  o.seg_instr = per;
+  Bisector B(nodes, o);
+  std::vector<int> items;
+  items.reserve(n);
+  for (int k = 0; k < n; ++k)
+    if (nodes[k].kind == K_ARITH || nodes[k].kind == K_OUTPUT) items.push_back(k);
+  const size_t n_items = items.size();
+  if (!items.empty()) B.split(items, false);
+  if (B.out.size() != n_items) { *err = "internal: schedule lost nodes"; return false; }
+  // merge adjacent small segments
+  std::vector<int> starts = B.seg_starts;
+  std::sort(starts.begin(), starts.end());
+  starts.erase(std::unique(starts.begin(), starts.end()), starts.end());
+  if (starts.empty() || starts[0] != 0) starts.insert(starts.begin(), 0);
+  std::vector<int> merged;
+  {
+    std::vector<int> ar(starts.size(), 0);
+    for (size_t s = 0; s < starts.size(); ++s) {
+      const int e = s + 1 < starts.size() ? starts[s + 1] : static_cast<int>(B.out.size());
+      for (int i = starts[s]; i < e; ++i) ar[s] += nodes[B.out[i]].kind == K_ARITH;
+    }
+    int cur = 0;
+    for (size_t s = 0; s < starts.size(); ++s) {
+      if (merged.empty() || cur + ar[s] > per) { merged.push_back(starts[s]); cur = ar[s]; }
+      else cur += ar[s];
+    }
+  }
+  // constants and inputs go right before their first reader (they are re-materialised by both kernel families)
+  std::vector<char> placed(n, 0);
+  S->order.reserve(n);
+  size_t ms = 0;
+  for (size_t i = 0; i < B.out.size(); ++i) {
+    if (ms < merged.size() && merged[ms] == static_cast<int>(i)) { S->seg_begin.push_back(static_cast<int>(S->order.size())); ++ms; }
+    const int v = B.out[i];
+    const int ops[2] = {nodes[v].a, nodes[v].b};
+    for (int u : ops)
+      if (u >= 0 && nodes[u].kind != K_ARITH && !placed[u]) { placed[u] = 1; S->order.push_back(u); }
+    placed[v] = 1;
+    S->order.push_back(v);
+  }
+  for (int k = 0; k < n; ++k)
+    if (!placed[k]) S->order.push_back(k);  // unread constants / inputs
+  if (S->seg_begin.empty()) S->seg_begin.push_back(0);
+  S->seg_begin.push_back(n);
+  // the order must be topological
+  std::vector<int> pos(n, -1);
+  if (static_cast<int>(S->order.size()) != n) { *err = "internal: schedule is not a permutation"; return false; }
+  for (int i = 0; i < n; ++i) pos[S->order[i]] = i;
+  for (int k = 0; k < n; ++k) {
+    if (pos[k] < 0) { *err = "internal: schedule is not a permutation"; return false; }
+    if ((nodes[k].a >= 0 && pos[nodes[k].a] >= pos[k]) || (nodes[k].b >= 0 && pos[nodes[k].b] >= pos[k])) {
+      *err = "internal: schedule violates a dependency";
+      return false;
+    }
+  }
+  S->cuts = B.cuts;
+  S->ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return true;
+}
+
+void permute_nodes(const std::vector<Node>& in, const std::vector<int>& order, std::vector<Node>* out) {
+  const int n = static_cast<int>(in.size());
+  std::vector<int> pos(n);
+  for (int i = 0; i < n; ++i) pos[order[i]] = i;
+  out->resize(n);
+  for (int i = 0; i < n; ++i) {
+    Node nd = in[order[i]];
+    if (nd.a >= 0) nd.a = pos[nd.a];
+    if (nd.b >= 0) nd.b = pos[nd.b];
+    (*out)[i] = nd;
+  }
+}
+
+void cross_traffic(const std::vector<Node>& nodes, const std::vector<int>& seg_begin, long long* loads, long long* stores) {
+  const int n = static_cast<int>(nodes.size());
+  std::vector<int> seg(n, 0);
+  for (size_t s = 0; s + 1 < seg_begin.size(); ++s)
+    for (int k = seg_begin[s]; k < seg_begin[s + 1]; ++k) seg[k] = static_cast<int>(s);
+  std::set<std::pair<int, int>> ld;
+  std::vector<char> st(n, 0);
+  for (int k = 0; k < n; ++k) {
+    const int ops[2] = {nodes[k].a, nodes[k].b};
+    for (int u : ops)
+      if (u >= 0 && nodes[u].kind == K_ARITH && seg[u] != seg[k]) { ld.insert({u, seg[k]}); st[u] = 1; }
+  }
+  *loads = static_cast<long long>(ld.size());
+  *stores = 0;
+  for (char c : st) *stores += c;
+}
+
+}  // namespace ccu

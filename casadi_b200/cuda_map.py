@@ -74,6 +74,18 @@ class CudaTape:
     def set_jit_plan(self, seg_instr=0, threads=0, min_blocks=-1, tile=-1):
         capi.check(capi.lib().ccu_tape_set_jit_plan(self.handle, seg_instr, threads, min_blocks, tile))
 
+    def set_jit_schedule(self, schedule):
+        """0 = reference tape order, 1 = min-cut bisection order (csrc/tape_schedule.hpp); takes effect at the
+        next (re)build of the specialised kernels."""
+        capi.check(capi.lib().ccu_tape_set_jit_schedule(self.handle, schedule))
+
+    def jit_plan_stats(self, seg_instr=0, schedule=-1):
+        """Plan of the specialisation (host only, nothing compiled)."""
+        st = (ctypes.c_longlong * 8)()
+        capi.check(capi.lib().ccu_tape_jit_plan_stats(self.handle, seg_instr, schedule, st))
+        return dict(segments=st[0], scratch_slots=st[1], cross_loads=st[2], cross_stores=st[3], max_segment=st[4],
+                    schedule_ms=st[5])
+
     def jit_sources(self):
         L = capi.lib()
         n = L.ccu_tape_get_jit_source(self.handle, -1, None, 0)

@@ -100,6 +100,8 @@ typedef struct ccu_tape_info {
   ccu_int jit_max_regs;   /* max registers per thread over the segments                              */
   ccu_int jit_cache_hits; /* segments served from the cubin cache                                    */
   ccu_int jit_threads;    /* CTA size of the specialised kernels                                     */
+  ccu_int jit_schedule;   /* 0 = reference order, 1 = min-cut bisection order (csrc/tape_schedule.hpp)       */
+  ccu_int jit_schedule_ms;/* time spent ordering and cutting the tape                                        */
 } ccu_tape_info;
 CCU_EXPORT int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info);
 
@@ -123,6 +125,14 @@ CCU_EXPORT int ccu_tape_set_jit_plan(ccu_tape* t, int seg_instr, int threads, in
 /* Generated CUDA source of segment `segment` (inspection/tests; works without a GPU): copies at most cap-1
  * characters, returns the full length; segment < 0 returns the number of segments. */
 CCU_EXPORT ccu_int ccu_tape_get_jit_source(const ccu_tape* t, ccu_int segment, char* buf, ccu_int cap);
+/* Plan of the specialisation for given options, computed on the host (works without a GPU; nothing is compiled or
+ * changed): seg_instr <= 0 / schedule < 0 keep the tape's current option.  The SXFunction tape order is the
+ * reference's depth-first order (sx_function.cpp:522-540); schedule 1 re-orders it (bit-identical results).
+ * stats = {segments, scratch slots, scratch reads per evaluation, scratch writes per evaluation,
+ *          largest segment (arithmetic instructions), schedule time in ms, 0, 0}. */
+CCU_EXPORT int ccu_tape_jit_plan_stats(const ccu_tape* t, int seg_instr, int schedule, ccu_int stats[8]);
+/* Selects the order used by subsequent (re)builds of the specialised kernels and by ccu_tape_get_jit_source. */
+CCU_EXPORT int ccu_tape_set_jit_schedule(ccu_tape* t, int schedule);
 
 /* Tunables of the plan (threads per CTA, instances per thread, shared slots); 0 = choose
  * automatically.  Replaces nothing in the reference: Map::create passes an empty Dict (map.cpp:43-47). */
