@@ -137,15 +137,33 @@ int build_plan(ccu_tape* t, int threads, int ipt, int slots_shared) {
   // automatic choice (B200 sweeps, profiles/r1_sweep_interp_v2.jsonl): keep the whole work vector in shared
   // memory when it is small; otherwise a SMALL shared window (occupancy beats fewer spills: 16 slots x 2 lanes
   // outran 48 x 1 by 1.9x on the quadrotor tape) and SPILL/FILL to the global scratch
-  const bool fits = t->max_live + 1 <= 32;
-  if (slots_shared <= 0) slots_shared = fits ? static_cast<int>(t->max_live + 1) : 16;
-  if (slots_shared < 4) slots_shared = 4;
-  opt.slots_shared = slots_shared;
+  // The instruction order is the min-cut bisection order (tape_schedule.hpp) unless CCU_SCHED=0: it keeps far fewer
+  // values alive at once than the reference's depth-first order, so more tapes fit the shared window entirely.
+  opt.schedule = 1;
+  if (const char* p = getenv("CCU_SCHED")) opt.schedule = atoi(p) ? 1 : 0;
   std::string err;
   ccu::Program prog;
-  if (!ccu::compile_tape(t->source(), opt, &prog, &err)) return fail("tape compile failed: %s", err.c_str());
+  bool fits;
+  if (slots_shared <= 0) {
+    opt.slots_shared = 32;
+    if (!ccu::compile_tape(t->source(), opt, &prog, &err)) return fail("tape compile failed: %s", err.c_str());
+    fits = prog.spill_loads == 0 && prog.spill_stores == 0;
+    if (!fits) {
+      opt.slots_shared = 16;
+      if (!ccu::compile_tape(t->source(), opt, &prog, &err)) return fail("tape compile failed: %s", err.c_str());
+    }
+  } else {
+    opt.slots_shared = std::max(slots_shared, 4);
+    if (!ccu::compile_tape(t->source(), opt, &prog, &err)) return fail("tape compile failed: %s", err.c_str());
+    fits = prog.spill_loads == 0 && prog.spill_stores == 0;
+  }
+  const bool auto_threads = threads <= 0, auto_ipt = ipt <= 0;
   if (threads <= 0) threads = fits ? 256 : 128;
   if (ipt <= 0) ipt = 2;  // two lanes per thread amortise the dispatch and give the FP64 pipe independent work
+  // a large window that holds the whole work vector: shrink the CTA until it fits the 227 KB
+  auto window = [&] { return static_cast<size_t>(prog.slots_shared) * threads * ipt * 8; };
+  if (auto_threads) while (window() > 200 * 1024 && threads > 64) threads /= 2;
+  if (auto_ipt) while (window() > 200 * 1024 && ipt > 1) ipt /= 2;
   if (threads % 32 != 0 || threads > 1024) return fail("plan: threads must be a multiple of 32, <= 1024");
   if (ipt != 1 && ipt != 2 && ipt != 4) return fail("plan: ipt must be 1, 2 or 4");
   if (ipt == 4 && threads > 512) return fail("plan: at most 512 threads with 4 instances per thread");
@@ -205,17 +223,21 @@ void jit_options_from_env(ccu::JitOptions* o) {
   if (const char* p = getenv("CCU_JIT_MINBLOCKS")) o->min_blocks = atoi(p);
   if (const char* p = getenv("CCU_JIT_BATCH")) o->load_batch = atoi(p);
   if (const char* p = getenv("CCU_JIT_TILE")) o->tile = atoll(p);
+  if (const char* p = getenv("CCU_JIT_STAGE")) o->stage = atoi(p);
+  if (const char* p = getenv("CCU_JIT_SPILL")) o->spill = atoi(p);
+  if (const char* p = getenv("CCU_JIT_REGVALS")) o->reg_values = atoi(p);
 }
 
 // (re)build the specialised kernels with the tape's current jit options
 int build_jit(ccu_tape* t) {
   if (t->device < 0) return fail("tape was compiled without a CUDA device");
-  if (t->jit_opt.threads % 32 != 0 || t->jit_opt.threads < 32 || t->jit_opt.threads > 1024)
+  const ccu::JitOptions eff = ccu::jit_resolve(t->jit_opt, t->flops);
+  if (eff.threads % 32 != 0 || eff.threads < 32 || eff.threads > 1024)
     return fail("jit: threads must be a multiple of 32 in [32, 1024]");
   CCU_CUDA(cudaSetDevice(t->device));
   ccu::JitProgram prog;
   std::string err;
-  if (!ccu::jit_build(t->source(), t->jit_opt, t->device, &prog, &err)) {
+  if (!ccu::jit_build(t->source(), eff, t->device, &prog, &err)) {
     t->jit_error = err;
     return fail("tape specialisation failed: %s", err.c_str());
   }
@@ -423,6 +445,7 @@ int ccu_tape_jit_plan_stats(const ccu_tape* t, int seg_instr, int schedule, ccu_
   ccu::JitOptions o = t->jit_opt;
   if (seg_instr > 0) o.seg_instr = seg_instr;
   if (schedule >= 0) o.schedule = schedule;
+  o = ccu::jit_resolve(o, t->flops);
   ccu::JitPlanStats ps;
   std::string err;
   if (!ccu::jit_plan_stats(t->source(), o, &ps, &err)) return fail("%s", err.c_str());
@@ -442,13 +465,14 @@ ccu_int ccu_tape_get_jit_source(const ccu_tape* t, ccu_int segment, char* buf, c
   if (!t) { fail("null tape"); return -1; }
   // generating re-plans the whole tape: keep the sources of the last option set
   char key[160];
-  snprintf(key, sizeof key, "%d,%d,%d,%d,%d", t->jit_opt.seg_instr, t->jit_opt.schedule, t->jit_opt.threads,
-           t->jit_opt.min_blocks, t->jit_opt.load_batch);
+  const ccu::JitOptions eff = ccu::jit_resolve(t->jit_opt, t->flops);
+  snprintf(key, sizeof key, "%d,%d,%d,%d,%d,%d,%d,%d", eff.seg_instr, eff.schedule, eff.threads, eff.min_blocks,
+           eff.load_batch, eff.stage, eff.spill, eff.reg_values);
   if (t->jit_src_key != key) {
     std::string err;
     t->jit_src.clear();
     t->jit_src_key.clear();
-    if (!ccu::jit_generate(t->source(), t->jit_opt, &t->jit_src, nullptr, &err)) { fail("%s", err.c_str()); return -1; }
+    if (!ccu::jit_generate(t->source(), eff, &t->jit_src, nullptr, &err)) { fail("%s", err.c_str()); return -1; }
     t->jit_src_key = key;
   }
   const std::vector<std::string>& src = t->jit_src;

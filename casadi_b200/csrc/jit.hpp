@@ -27,11 +27,14 @@
 namespace ccu {
 
 struct JitOptions {
-  int seg_instr = 800;    // arithmetic instructions per segment
+  int seg_instr = 0;      // arithmetic instructions per segment; 0 = automatic (jit_resolve)
   int schedule = 1;       // 0 = reference order, fixed-length segments; 1 = min-cut bisection (tape_schedule.hpp)
-  int threads = 256;      // CTA size
-  int min_blocks = 2;     // __launch_bounds__ second argument: 2 CTAs of 256 threads per SM = at most 128 registers (0 = up to 255)
-  int load_batch = 8;     // cross-segment live-ins are loaded in groups of this many (memory-level parallelism)
+  int threads = 0;        // CTA size; 0 = automatic
+  int min_blocks = -1;    // __launch_bounds__ second argument (resident CTAs per SM, bounds the registers); 0 = none, -1 = automatic
+  int load_batch = 32;    // cross-segment live-ins read straight from global memory are loaded in groups of this many
+  int stage = 0;          // live-ins per segment staged in shared memory by TMA bulk copies: -1 = as many as fit, 0 = off
+  int spill = 0;          // private shared-memory rows for values that do not fit the registers: -1 = what is left, 0 = off
+  int reg_values = 0;     // doubles planned in registers (0 = from the launch bounds)
   int compile_threads = 0;  // 0 = hardware concurrency (max 32)
   long long tile = 0;     // instances per tile (0 = automatic)
   std::string cache_dir;  // compiled cubins are cached here ("" = $CCU_JIT_CACHE or ~/.cache/casadi_cuda)
@@ -40,16 +43,24 @@ struct JitOptions {
 struct JitProgram {
   std::vector<cudaLibrary_t> libs;
   std::vector<cudaKernel_t> kernels;
+  std::vector<int> smem_bytes;  // dynamic shared memory of each kernel (staged live-ins + mbarriers)
   int threads = 128;
   int scratch_slots = 0;        // cross-segment values alive at once (per instance)
   long long tile = 0;           // instances per tile (0 = whole batch in one tile)
   long long cross_loads = 0;    // scratch reads per evaluation
   long long cross_stores = 0;   // scratch writes per evaluation
+  long long smem_moves = 0;     // shared-memory spill stores + reloads per evaluation
   int max_regs = 0;             // max registers per thread over the segments
   int cache_hits = 0;
   double compile_ms = 0;
   double schedule_ms = 0;       // time spent ordering / cutting the tape (tape_schedule.hpp)
 };
+
+// Fills in the automatic fields from the tape's size (B200 sweeps, profiles/r1_sweep_sched.jsonl): a tape of up to
+// 8000 arithmetic instructions is ONE kernel with 2 x 256 threads per SM (<= 128 registers; the minimum cuts make
+// its work vector fit); longer tapes are cut every ~2000 instructions and run 2 x 128 threads per SM with up to 255
+// registers, because their segments hold 100-200 values alive at once.
+JitOptions jit_resolve(const JitOptions& opt, long long flops);
 
 // true when libnvrtc can be loaded in this process
 bool jit_available(std::string* why);

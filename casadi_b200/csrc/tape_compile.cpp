@@ -5,10 +5,10 @@
 // the compiler (1) recovers the value graph (SSA) from the slot stream, (2) re-allocates values to
 // at most `slots_shared` shared slots with furthest-next-use eviction, inserting SPILL/FILL moves to
 // a per-instance global scratch and re-materialising constants/inputs, and (3) forwards a value
-// consumed only by the next instruction through a register (F_ACC/D_NONE).  The ORDER of the
-// arithmetic instructions and every operand pairing is preserved: each value is computed by the same
-// operation from the same operand values as in SXFunction::eval (sx_function.cpp:111-124), so
-// results are bit-identical whatever the allocation.
+// consumed only by the next instruction through a register (F_ACC/D_NONE).  Every operand pairing is
+// preserved: each value is computed by the same operation from the same operand values as in
+// SXFunction::eval (sx_function.cpp:111-124), so results are bit-identical whatever the allocation and
+// whatever topological order the instructions are issued in (CompileOptions::schedule).
 #include "tape_compile.hpp"
 
 #include <algorithm>
@@ -16,6 +16,7 @@
 #include <set>
 
 #include "ccu_isa.h"
+#include "tape_schedule.hpp"
 
 namespace ccu {
 namespace {
@@ -176,6 +177,17 @@ bool compile_tape(const TapeSource& src, const CompileOptions& opt, Program* out
   std::vector<Node> nodes;
   long long flops = 0;
   if (!build_graph(src, &nodes, &flops, err)) return false;
+  if (opt.schedule == 1) {
+    // any topological order computes the same bits; this one keeps the live set small (tape_schedule.hpp)
+    ScheduleOptions so;
+    so.method = 1;
+    so.seg_instr = 1 << 30;
+    Schedule sch;
+    if (!schedule_tape(nodes, so, &sch, err)) return false;
+    std::vector<Node> ordered;
+    permute_nodes(nodes, sch.order, &ordered);
+    nodes.swap(ordered);
+  }
   const int n = static_cast<int>(nodes.size());
   const int S = opt.slots_shared;
   if (S < 4) { *err = "slots_shared must be >= 4"; return false; }

@@ -22,7 +22,7 @@ struct TapeSource {
 struct CompileOptions {
   int slots_shared = 0;   // shared-memory work slots per instance available to the allocator (>=4)
   bool use_acc = true;    // forward the previous result in a register (F_ACC / D_NONE)
-  int schedule = 0;       // 0 = reference order
+  int schedule = 0;       // 0 = reference order, 1 = min-cut bisection order (tape_schedule.hpp)
 };
 
 struct Program {

@@ -5,6 +5,10 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <set>
 #include <utility>
 
@@ -12,6 +16,8 @@ namespace ccu {
 namespace {
 
 constexpr int kInf = 1 << 28;
+
+struct PieceRec { int begin, end, arith; };
 
 // Dinic's maximum flow on a forward-star graph; blocking flows are found iteratively (dependency chains make
 // augmenting paths thousands of edges long).
@@ -118,7 +124,7 @@ struct Bisector {
   std::vector<int> ext_z;         // external value -> flow node of the current network (-1 = none, -2 = constant)
   std::vector<int> ext_touched;
   std::vector<int> out;           // items in final order
-  std::vector<int> seg_starts;    // indices into `out`
+  std::vector<PieceRec> pieces;   // every piece of the recursion: [begin, end) in `out`, arithmetic instructions
   FlowNet net;
   long long cuts = 0;
 
@@ -222,14 +228,11 @@ struct Bisector {
     for (int v : piece) { out.push_back(v); done[v] = 1; }
   }
 
-  void split(std::vector<int>& piece, bool in_seg) {
+  void split(std::vector<int>& piece) {
     const int m = static_cast<int>(piece.size());
-    if (!in_seg && arith_count(piece) <= opt.seg_instr) {
-      seg_starts.push_back(static_cast<int>(out.size()));
-      in_seg = true;
-    }
-    if (m <= 2 || (in_seg && m <= std::max(opt.min_piece, 4))) {
-      if (!in_seg) seg_starts.push_back(static_cast<int>(out.size()));
+    const int begin = static_cast<int>(out.size());
+    pieces.push_back({begin, begin + m, arith_count(piece)});
+    if (m <= std::max(opt.min_piece, 2)) {
       emit(piece);
       return;
     }
@@ -265,15 +268,22 @@ struct Bisector {
     for (int i = 0; i < m; ++i) (d[i] ? A : B).push_back(piece[i]);
     std::vector<int>().swap(piece);
     if (A.empty() || B.empty()) {  // cannot happen with pins on both sides; keep the order rather than loop
-      std::vector<int>& all = A.empty() ? B : A;
-      if (!in_seg) seg_starts.push_back(static_cast<int>(out.size()));
-      emit(all);
+      emit(A.empty() ? B : A);
       return;
     }
-    split(A, in_seg);
-    split(B, in_seg);
+    split(A);
+    split(B);
   }
 };
+
+struct Recursion {
+  int n = 0;
+  std::vector<int> out;
+  std::vector<PieceRec> pieces;
+  long long cuts = 0;
+};
+std::mutex g_cache_mutex;
+std::deque<std::pair<uint64_t, std::shared_ptr<const Recursion>>> g_cache;
 
 }  // namespace
 
@@ -292,41 +302,69 @@ bool schedule_tape(const std::vector<Node>& nodes, const ScheduleOptions& opt, S
     S->seg_begin.push_back(n);
     return true;
   }
+  // the recursion does not depend on seg_instr: it is computed once per tape and kept (a tape is planned several
+  // times: interpreter order, specialised kernels, re-plans with other segment lengths)
   ScheduleOptions o = opt;
-  o.seg_instr = per;
-  Bisector B(nodes, o);
-  std::vector<int> items;
-  items.reserve(n);
-  for (int k = 0; k < n; ++k)
-    if (nodes[k].kind == K_ARITH || nodes[k].kind == K_OUTPUT) items.push_back(k);
-  const size_t n_items = items.size();
-  if (!items.empty()) B.split(items, false);
-  if (B.out.size() != n_items) { *err = "internal: schedule lost nodes"; return false; }
-  // merge adjacent small segments
-  std::vector<int> starts = B.seg_starts;
-  std::sort(starts.begin(), starts.end());
-  starts.erase(std::unique(starts.begin(), starts.end()), starts.end());
-  if (starts.empty() || starts[0] != 0) starts.insert(starts.begin(), 0);
+  o.min_piece = std::min(opt.min_piece, std::max(2, per / 2));  // (tiny segments are only asked for by tests)
+  uint64_t key = 1469598103934665603ull;
+  auto mix = [&](uint64_t v) { key ^= v; key *= 1099511628211ull; };
+  mix(static_cast<uint64_t>(n)); mix(static_cast<uint64_t>(o.min_piece)); mix(static_cast<uint64_t>(opt.pin_frac * 1e6));
+  for (const Node& nd : nodes) {
+    uint64_t cb;
+    std::memcpy(&cb, &nd.c, 8);
+    mix((static_cast<uint64_t>(nd.kind) << 8) | nd.dop); mix(static_cast<uint64_t>(static_cast<uint32_t>(nd.a)));
+    mix(static_cast<uint64_t>(static_cast<uint32_t>(nd.b))); mix((static_cast<uint64_t>(nd.idx) << 32) | static_cast<uint32_t>(nd.nz));
+    mix(cb);
+  }
+  std::shared_ptr<const Recursion> rec;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    for (auto& e : g_cache)
+      if (e.first == key && e.second->n == n) { rec = e.second; break; }
+  }
+  if (!rec) {
+    Bisector B(nodes, o);
+    std::vector<int> items;
+    items.reserve(n);
+    for (int k = 0; k < n; ++k)
+      if (nodes[k].kind == K_ARITH || nodes[k].kind == K_OUTPUT) items.push_back(k);
+    const size_t n_items = items.size();
+    if (!items.empty()) B.split(items);
+    if (B.out.size() != n_items) { *err = "internal: schedule lost nodes"; return false; }
+    auto r = std::make_shared<Recursion>();
+    r->n = n;
+    r->out = std::move(B.out);
+    r->pieces = std::move(B.pieces);
+    r->cuts = B.cuts;
+    rec = r;
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    g_cache.push_front({key, rec});
+    if (g_cache.size() > 16) g_cache.pop_back();
+  }
+  const std::vector<int>& out = rec->out;
+  // segments: the maximal pieces with at most `per` arithmetic instructions (pieces are in pre-order, so a piece
+  // inside an accepted one starts before that one's end); adjacent small ones are merged
   std::vector<int> merged;
   {
-    std::vector<int> ar(starts.size(), 0);
-    for (size_t s = 0; s < starts.size(); ++s) {
-      const int e = s + 1 < starts.size() ? starts[s + 1] : static_cast<int>(B.out.size());
-      for (int i = starts[s]; i < e; ++i) ar[s] += nodes[B.out[i]].kind == K_ARITH;
+    std::vector<std::pair<int, int>> segs;  // (begin, arith)
+    int covered = 0;
+    for (const PieceRec& pc : rec->pieces) {
+      if (pc.begin < covered) continue;
+      if (pc.arith <= per || pc.end - pc.begin <= 2) { segs.push_back({pc.begin, pc.arith}); covered = pc.end; }
     }
     int cur = 0;
-    for (size_t s = 0; s < starts.size(); ++s) {
-      if (merged.empty() || cur + ar[s] > per) { merged.push_back(starts[s]); cur = ar[s]; }
-      else cur += ar[s];
+    for (const auto& sgm : segs) {
+      if (merged.empty() || cur + sgm.second > per) { merged.push_back(sgm.first); cur = sgm.second; }
+      else cur += sgm.second;
     }
   }
   // constants and inputs go right before their first reader (they are re-materialised by both kernel families)
   std::vector<char> placed(n, 0);
   S->order.reserve(n);
   size_t ms = 0;
-  for (size_t i = 0; i < B.out.size(); ++i) {
+  for (size_t i = 0; i < out.size(); ++i) {
     if (ms < merged.size() && merged[ms] == static_cast<int>(i)) { S->seg_begin.push_back(static_cast<int>(S->order.size())); ++ms; }
-    const int v = B.out[i];
+    const int v = out[i];
     const int ops[2] = {nodes[v].a, nodes[v].b};
     for (int u : ops)
       if (u >= 0 && nodes[u].kind != K_ARITH && !placed[u]) { placed[u] = 1; S->order.push_back(u); }
@@ -348,7 +386,7 @@ bool schedule_tape(const std::vector<Node>& nodes, const ScheduleOptions& opt, S
       return false;
     }
   }
-  S->cuts = B.cuts;
+  S->cuts = rec->cuts;
   S->ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return true;
 }

@@ -25,12 +25,17 @@ def test_library_exports_every_declared_symbol():
     assert L.ccu_abi_version() == 2
 
 
-def emulate(tape_name, case_name, S, nmax=64):
+def emulate(tape_name, case_name, S, nmax=64, sched=None):
     tape = load_tape(tape_name)
     case = load_case(case_name)
     N = min(case["N"], nmax)
-    t = CudaTape(tape, device=-1)
-    t.set_plan(128, 1, S)
+    if sched is not None:
+        os.environ["CCU_SCHED"] = str(sched)
+    try:
+        t = CudaTape(tape, device=-1)
+        t.set_plan(128, 1, S)
+    finally:
+        os.environ.pop("CCU_SCHED", None)
     info = t.info()
     ins = [a[:N * n] for a, n in zip(case["in"], t.nnz_in)]
     outs = run_program(t.program(), N, t.nnz_in, t.nnz_out, ins, info["slots_shared"], info["slots_global"])
@@ -52,12 +57,22 @@ def test_automatic_plan_small_window_for_large_work_vectors():
     assert info["slots_shared"] == 16 and info["slots_global"] > 0
 
 
+@pytest.mark.parametrize("sched", [0, 1])
 @pytest.mark.parametrize("name,S", [("cartpole", 4), ("cartpole", 8), ("cartpole", 16), ("quad1", 6), ("quad1", 24),
-                                    ("quad", 48), ("quad", 16), ("mc", 32), ("quad1_jac", 32), ("mapnode", 4)])
-def test_compiled_program_with_spills(name, S):
-    info = emulate(name, name, S, nmax=24)
+                                    ("quad", 48), ("quad", 16), ("mc", 8), ("quad1_jac", 32), ("mapnode", 4)])
+def test_compiled_program_with_spills(name, S, sched):
+    """Both instruction orders (reference depth-first / min-cut bisection) reproduce the reference bits."""
+    info = emulate(name, name, S, nmax=24, sched=sched)
     if name != "mapnode":
         assert info["slots_global"] > 0 and info["spill_loads"] > 0
+
+
+def test_bisection_order_shrinks_the_live_set():
+    # mapaccum T=100 (reference order: 388 values spilled with a 16-slot window) fits 32 shared slots entirely, and
+    # the 20-step quadrotor integrator (591 live values in reference order) fits 64
+    assert emulate("mc", "mc", 32, nmax=8, sched=1)["slots_global"] == 0
+    assert emulate("mc", "mc", 32, nmax=8, sched=0)["slots_global"] > 0
+    assert emulate("quad", "quad", 64, nmax=8, sched=1)["slots_global"] == 0
 
 
 @pytest.mark.parametrize("name", ["quad_fwd", "quad_adj", "rocket_hess"])

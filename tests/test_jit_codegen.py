@@ -29,6 +29,17 @@ SHIM = r"""
 static inline double __longlong_as_double(long long x) { double d; std::memcpy(&d, &x, 8); return d; }
 struct ccu_dim3 { unsigned x, y, z; };
 static ccu_dim3 blockIdx, blockDim, threadIdx;
+// staged live-ins (TMA bulk copy -> shared memory on the device) read the scratch slot directly on the host
+static double ccu_host_sm[8192];  // private shared-memory rows: one host "thread" runs at a time
+#define CCU_SM_DECL
+#define CCU_SM_ST(r, v) ccu_host_sm[r] = (v)
+#define CCU_SM_LD(r) ccu_host_sm[r]
+#define CCU_STAGE_DECL
+#define CCU_STAGE_INIT
+#define CCU_STAGE_ARM(g, n)
+#define CCU_STAGE_COPY(j, s, g)
+#define CCU_STAGE_WAIT(g)
+#define CCU_STAGE_LD(j, s) CCU_LD(s)
 """
 DRIVER = r"""
 extern "C" void run_seg(const ccu::IoDesc* io, long long inst0, long long n_tile, double* sc, long long sstride) {

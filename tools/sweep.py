@@ -39,6 +39,12 @@ def run(name, N, plans, reps=3):
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cartpole", "quad", "quad_jac"]
+    if "v3" in which:  # with the min-cut bisection order larger shared windows hold (almost) the whole live set
+        run("quad", 1 << 20, [(128, 2, 16), (128, 2, 32), (128, 2, 48), (128, 1, 64), (128, 2, 64), (256, 1, 64), (64, 2, 64), (64, 4, 64)])
+        run("quad_jac", 1 << 18, [(128, 2, 16), (128, 2, 24), (128, 2, 32), (128, 2, 48), (128, 1, 64), (128, 2, 64), (128, 1, 96), (128, 2, 96), (64, 2, 96)], reps=2)
+        run("rocket_hess", 1 << 18, [(128, 2, 16), (128, 2, 32), (128, 2, 64), (128, 1, 96)], reps=2)
+        run("mc", 1 << 20, [(0, 0, 0), (128, 2, 16), (256, 2, 20), (256, 1, 20), (128, 4, 20)], reps=2)
+        sys.exit(0)
     if "cartpole" in which:
         run("cartpole", 1 << 22, [(128, 1, 0), (128, 2, 0), (128, 4, 0), (256, 1, 0), (256, 2, 0), (64, 2, 0), (64, 4, 0),
                                   (512, 1, 0), (32, 4, 0), (256, 4, 0), (512, 2, 0), (1024, 1, 0)])
