@@ -339,7 +339,7 @@ def main_cuda(args):
                 "roofline_evals_per_s": 1.0 / max(t_fp64, t_hbm),
                 "scratch": {"bytes_per_eval": scratch_bytes, "achieved": scratch_bytes * N / (jac_ms * 1e-3) / 1e9,
                             "unit": "GB/s", "frac_of_hbm_peak": scratch_bytes * N / (jac_ms * 1e-3) / 1e9 / hbm_peak,
-                            "note": "work-vector traffic of the 2625-live-value tape through HBM; not algorithmic bytes"}}
+                            "note": "cross-segment work-vector traffic through HBM (scratch loads + stores of the plan); not algorithmic bytes"}}
     cpu = None
     if not args.no_cpu and world == 1:
         try:

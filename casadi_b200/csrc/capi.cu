@@ -196,7 +196,8 @@ int ensure_scratch(ccu_tape* t) {
 int launch(ccu_tape* t, const ccu::IoDesc& io, long long N, cudaStream_t stream) {
   if (t->mode == CCU_MODE_JIT) {
     const long long tile = ccu::jit_tile_for(t->jit, N, t->sms);
-    if (t->jit.scratch_slots > 0 && t->scratch.ensure(static_cast<size_t>(t->jit.scratch_slots) * tile)) return 1;
+    if (t->jit.scratch_slots > 0 &&
+        t->scratch.ensure(static_cast<size_t>(t->jit.scratch_slots) * tile * std::max(1, t->jit.streams))) return 1;
     if (t->ev0) cudaEventRecord(t->ev0, stream);
     long long nl = 0;
     cudaError_t e = ccu::jit_launch(t->jit, io, N, t->scratch.p, tile, stream, &nl);
@@ -223,6 +224,7 @@ void jit_options_from_env(ccu::JitOptions* o) {
   if (const char* p = getenv("CCU_JIT_MINBLOCKS")) o->min_blocks = atoi(p);
   if (const char* p = getenv("CCU_JIT_BATCH")) o->load_batch = atoi(p);
   if (const char* p = getenv("CCU_JIT_TILE")) o->tile = atoll(p);
+  if (const char* p = getenv("CCU_JIT_STREAMS")) o->streams = atoi(p);
   if (const char* p = getenv("CCU_JIT_STAGE")) o->stage = atoi(p);
   if (const char* p = getenv("CCU_JIT_SPILL")) o->spill = atoi(p);
   if (const char* p = getenv("CCU_JIT_REGVALS")) o->reg_values = atoi(p);

@@ -37,6 +37,7 @@ struct JitOptions {
   int reg_values = 0;     // doubles planned in registers (0 = from the launch bounds)
   int compile_threads = 0;  // 0 = hardware concurrency (max 32)
   long long tile = 0;     // instances per tile (0 = automatic)
+  int streams = 1;        // tiles in flight at once (each on its own stream and scratch region)
   std::string cache_dir;  // compiled cubins are cached here ("" = $CCU_JIT_CACHE or ~/.cache/casadi_cuda)
 };
 
@@ -47,6 +48,10 @@ struct JitProgram {
   int threads = 128;
   int scratch_slots = 0;        // cross-segment values alive at once (per instance)
   long long tile = 0;           // instances per tile (0 = whole batch in one tile)
+  int streams = 1;              // tiles in flight at once
+  std::vector<cudaStream_t> side;    // created on first use
+  std::vector<cudaEvent_t> side_done;
+  cudaEvent_t fork = nullptr;
   long long cross_loads = 0;    // scratch reads per evaluation
   long long cross_stores = 0;   // scratch writes per evaluation
   long long smem_moves = 0;     // shared-memory spill stores + reloads per evaluation
@@ -83,7 +88,7 @@ bool jit_plan_stats(const TapeSource& src, const JitOptions& opt, JitPlanStats* 
 long long jit_tile_for(const JitProgram& p, long long N, int sms);
 
 // scratch must hold scratch_slots * jit_tile_for(N) doubles
-cudaError_t jit_launch(const JitProgram& p, const IoDesc& io, long long N, double* scratch, long long tile,
+cudaError_t jit_launch(JitProgram& p, const IoDesc& io, long long N, double* scratch, long long tile,
                        cudaStream_t stream, long long* launches);
 
 void jit_destroy(JitProgram* p);

@@ -1,0 +1,70 @@
+"""CPU-only tests of the tape scheduler (casadi_b200/csrc/tape_schedule.cpp): the min-cut bisection order is a valid
+topological order (bit-exactness of the programs built from it is pinned in test_compile.py / test_jit_codegen.py),
+its segments respect the requested length, and it cuts far fewer values than the reference's depth-first order
+(SXFunction::init, casadi/core/sx_function.cpp:522-540) on the time-stepping tapes of BASELINE.json."""
+import os
+
+import pytest
+
+from casadi_b200 import CudaTape, load_tape
+from test_jit_codegen import run_generated
+from util import assert_bit_equal
+
+
+def stats(name, seg, sched):
+    return CudaTape(load_tape(name), device=-1).jit_plan_stats(seg, sched)
+
+
+@pytest.mark.parametrize("name,seg", [("quad", 800), ("quad", 2000), ("mc", 800), ("rocket_hess", 800), ("quad1_jac", 300)])
+def test_bisection_cuts_fewer_values_than_the_reference_order(name, seg):
+    ref, bis = stats(name, seg, 0), stats(name, seg, 1)
+    assert bis["max_segment"] <= seg and ref["max_segment"] <= seg
+    assert bis["cross_loads"] + bis["cross_stores"] < ref["cross_loads"] + ref["cross_stores"]
+    assert bis["scratch_slots"] <= ref["scratch_slots"]
+
+
+def test_quadrotor_integrator_cuts_are_the_state_vector():
+    # 20 RK4 steps of a 12-state model: every cut of the bisection order carries the 12 states (reference order: 919
+    # loads and 741 stores over 9 segments because values of all 20 steps stay alive)
+    s = stats("quad", 4000, 1)
+    assert s["segments"] == 2 and s["cross_loads"] == 12 and s["cross_stores"] == 12 and s["scratch_slots"] == 12
+    assert stats("quad", 8000, 1)["segments"] == 1
+
+
+def test_mapaccum_tape_cuts_are_the_carried_state():
+    s = stats("mc", 2000, 1)  # T=100 mapaccum of a 4-state leaf + running cost: 5 values cross the cut
+    assert s["segments"] == 2 and s["cross_loads"] == 5 and s["cross_stores"] == 5
+
+
+def test_schedule_is_deterministic_and_cached():
+    t = CudaTape(load_tape("quad"), device=-1)
+    a = t.jit_plan_stats(800, 1)
+    b = t.jit_plan_stats(800, 1)
+    assert {k: v for k, v in a.items() if k != "schedule_ms"} == {k: v for k, v in b.items() if k != "schedule_ms"}
+    assert b["schedule_ms"] <= a["schedule_ms"]
+
+
+def test_automatic_plan_sizes():
+    assert stats("cartpole", 0, 1)["segments"] == 1
+    assert stats("quad", 0, 1)["segments"] == 1          # <= 8000 arithmetic instructions: one kernel
+    s = stats("rocket_hess", 0, 1)                        # longer: cut every ~2000
+    assert s["segments"] > 1 and s["max_segment"] <= 2000
+
+
+@pytest.mark.parametrize("sched", ["0", "1"])
+@pytest.mark.parametrize("opts", [{}, {"CCU_JIT_REGVALS": "6", "CCU_JIT_SPILL": "-1"}, {"CCU_JIT_REGVALS": "5", "CCU_JIT_SPILL": "3", "CCU_JIT_STAGE": "2"},
+                                  {"CCU_JIT_STAGE": "-1"}])
+def test_generated_code_variants_reproduce_reference_bits(sched, opts):
+    """Reference / bisection order x (plain, shared-memory spill rows, spill rows + staged live-ins + compiler-managed
+    overflow, everything staged): the generated segments reproduce the reference bits on the host."""
+    env = dict(opts, CCU_JIT_SCHED=sched)
+    os.environ.update(env)
+    try:
+        for tape, seg in (("quad1_jac", 300), ("mc", 500)):
+            nseg, outs, want = run_generated(tape, tape, seg, nmax=12)
+            assert nseg > 1
+            for j, (g, w) in enumerate(zip(outs, want)):
+                assert_bit_equal(g, w, "%s %s out%d" % (tape, env, j))
+    finally:
+        for k in env:
+            os.environ.pop(k, None)

@@ -13,7 +13,7 @@ tape, case = load_tape(name), load_case(name)
 t = CudaTape(tape, mode="interp")
 if seg > 0:
     t.set_jit_schedule(sched)
-    t.set_jit_plan(seg, threads, minb, 0)
+    t.set_jit_plan(seg, threads, minb, int(os.environ.get("TILE", "0")))
 dev = torch.device("cuda:0")
 P = case["N"]
 d_in = []
