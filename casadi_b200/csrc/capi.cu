@@ -225,6 +225,7 @@ void jit_options_from_env(ccu::JitOptions* o) {
   if (const char* p = getenv("CCU_JIT_BATCH")) o->load_batch = atoi(p);
   if (const char* p = getenv("CCU_JIT_TILE")) o->tile = atoll(p);
   if (const char* p = getenv("CCU_JIT_STREAMS")) o->streams = atoi(p);
+  if (const char* p = getenv("CCU_JIT_PREFETCH")) o->prefetch = atoi(p);
   if (const char* p = getenv("CCU_JIT_STAGE")) o->stage = atoi(p);
   if (const char* p = getenv("CCU_JIT_SPILL")) o->spill = atoi(p);
   if (const char* p = getenv("CCU_JIT_REGVALS")) o->reg_values = atoi(p);
@@ -452,7 +453,7 @@ int ccu_tape_jit_plan_stats(const ccu_tape* t, int seg_instr, int schedule, ccu_
   std::string err;
   if (!ccu::jit_plan_stats(t->source(), o, &ps, &err)) return fail("%s", err.c_str());
   stats[0] = ps.segments; stats[1] = ps.scratch_slots; stats[2] = ps.cross_loads; stats[3] = ps.cross_stores;
-  stats[4] = ps.max_segment; stats[5] = static_cast<ccu_int>(ps.schedule_ms); stats[6] = 0; stats[7] = 0;
+  stats[4] = ps.max_segment; stats[5] = static_cast<ccu_int>(ps.schedule_ms); stats[6] = ps.max_live; stats[7] = static_cast<ccu_int>(ps.mean_live);
   return 0;
 }
 
@@ -468,8 +469,8 @@ ccu_int ccu_tape_get_jit_source(const ccu_tape* t, ccu_int segment, char* buf, c
   // generating re-plans the whole tape: keep the sources of the last option set
   char key[160];
   const ccu::JitOptions eff = ccu::jit_resolve(t->jit_opt, t->flops);
-  snprintf(key, sizeof key, "%d,%d,%d,%d,%d,%d,%d,%d", eff.seg_instr, eff.schedule, eff.threads, eff.min_blocks,
-           eff.load_batch, eff.stage, eff.spill, eff.reg_values);
+  snprintf(key, sizeof key, "%d,%d,%d,%d,%d,%d,%d,%d,%d", eff.seg_instr, eff.schedule, eff.threads, eff.min_blocks,
+           eff.load_batch, eff.stage, eff.spill, eff.reg_values, eff.prefetch);
   if (t->jit_src_key != key) {
     std::string err;
     t->jit_src.clear();

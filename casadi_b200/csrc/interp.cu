@@ -14,7 +14,7 @@
 //     diverges: SX tapes are straight-line, if_else is arithmetic;
 //   * the work vector lives in shared memory as w[slot][lane]: lane-contiguous, hence bank-conflict-free
 //     64-bit accesses; values the allocator could not keep in the shared slots are moved by FILL/SPILL to a
-//     global scratch laid out [slot][resident lane] (coalesced);
+//     global scratch laid out [CTA][slot][lane] (coalesced);
 //   * the previous result is forwarded in a register (X_ACC / X_NONE); the hot operations (+,-,*, neg, sq,
 //     twice) have one switch case per operand-source combination, so their bodies are LDS/LDS/DADD/STS;
 //   * persistent grid: each CTA loops over tiles of threads*IPT instances, so the scratch is sized by the
@@ -109,7 +109,8 @@ __device__ __noinline__ double libm_binary(uint32_t op, double x, double y) {
 template <int IPT, bool SCRATCH>
 __global__ void __launch_bounds__(IPT >= 4 ? 512 : 1024) ccu_interp_kernel(const XInstr* __restrict__ prog, const int nchunks, const IoDesc io,
                                                           const long long N, double* __restrict__ scratch,
-                                                          const long long ntiles, const uint32_t stage_off) {
+                                                          const long long ntiles, const uint32_t stage_off,
+                                                          const int slots_global) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int BD = blockDim.x;
   const int WS = IPT * BD;  // lanes per CTA
@@ -120,8 +121,10 @@ __global__ void __launch_bounds__(IPT >= 4 ? 512 : 1024) ccu_interp_kernel(const
   const uint32_t lane_stride = static_cast<uint32_t>(BD) * 8u;
   const uint32_t stage0 = s_base + stage_off;
   const uint32_t bar0 = stage0 + 2u * kStageBytes;
-  const long long scratch_stride = (long long)gridDim.x * WS;
-  double* const my_scratch = scratch + (long long)blockIdx.x * WS + tid;
+  // blocked by CTA, [CTA][slot][lane]: a CTA's scratch is one contiguous region (the flat [slot][all lanes] layout put
+  // consecutive slots megabytes apart: a TLB entry per slot)
+  const long long scratch_stride = WS;
+  double* const my_scratch = scratch + (long long)blockIdx.x * ((long long)slots_global * WS) + tid;
 
   if (tid == 0) {
     mbar_init(bar0, 1);
@@ -386,7 +389,7 @@ cudaError_t launch_interp(const LaunchPlan& plan, const XInstr* d_prog, long lon
   const uint32_t stage_off = static_cast<uint32_t>(plan.smem_bytes - 2 * kStageBytes - 16);
 #define CCU_LAUNCH(I, S)                                                                                              \
   ccu_interp_kernel<I, S><<<grid, plan.threads, plan.smem_bytes, stream>>>(d_prog, nchunks, io, N, d_scratch, ntiles, \
-                                                                           stage_off)
+                                                                           stage_off, plan.slots_global)
   switch (plan.ipt) {
     case 1: if (sc) CCU_LAUNCH(1, true); else CCU_LAUNCH(1, false); break;
     case 2: if (sc) CCU_LAUNCH(2, true); else CCU_LAUNCH(2, false); break;

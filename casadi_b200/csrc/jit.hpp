@@ -32,6 +32,7 @@ struct JitOptions {
   int threads = 0;        // CTA size; 0 = automatic
   int min_blocks = -1;    // __launch_bounds__ second argument (resident CTAs per SM, bounds the registers); 0 = none, -1 = automatic
   int load_batch = 32;    // cross-segment live-ins read straight from global memory are loaded in groups of this many
+  int prefetch = 0;       // 1 / 2: prefetch.global.L2 / .L1 of every live-in (and dense inputs) at kernel entry
   int stage = 0;          // live-ins per segment staged in shared memory by TMA bulk copies: -1 = as many as fit, 0 = off
   int spill = 0;          // private shared-memory rows for values that do not fit the registers: -1 = what is left, 0 = off
   int reg_values = 0;     // doubles planned in registers (0 = from the launch bounds)
@@ -80,6 +81,8 @@ bool jit_generate(const TapeSource& src, const JitOptions& opt, std::vector<std:
 // the plan alone (host only): segments, scratch slots and traffic for the given options
 struct JitPlanStats {
   long long segments = 0, scratch_slots = 0, cross_loads = 0, cross_stores = 0, max_segment = 0;
+  long long max_live = 0;  // peak number of values alive inside one segment, maximum over the segments
+  double mean_live = 0;    // the same, mean over the segments
   double schedule_ms = 0;
 };
 bool jit_plan_stats(const TapeSource& src, const JitOptions& opt, JitPlanStats* out, std::string* err);

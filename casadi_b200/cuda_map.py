@@ -84,7 +84,7 @@ class CudaTape:
         st = (ctypes.c_longlong * 8)()
         capi.check(capi.lib().ccu_tape_jit_plan_stats(self.handle, seg_instr, schedule, st))
         return dict(segments=st[0], scratch_slots=st[1], cross_loads=st[2], cross_stores=st[3], max_segment=st[4],
-                    schedule_ms=st[5])
+                    schedule_ms=st[5], max_live=st[6], mean_live=st[7])
 
     def jit_sources(self):
         L = capi.lib()

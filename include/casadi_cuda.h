@@ -129,7 +129,8 @@ CCU_EXPORT ccu_int ccu_tape_get_jit_source(const ccu_tape* t, ccu_int segment, c
  * changed): seg_instr <= 0 / schedule < 0 keep the tape's current option.  The SXFunction tape order is the
  * reference's depth-first order (sx_function.cpp:522-540); schedule 1 re-orders it (bit-identical results).
  * stats = {segments, scratch slots, scratch reads per evaluation, scratch writes per evaluation,
- *          largest segment (arithmetic instructions), schedule time in ms, 0, 0}. */
+ *          largest segment (arithmetic instructions), schedule time in ms,
+ *          peak values alive inside one segment (max over segments), the same (mean over segments)}. */
 CCU_EXPORT int ccu_tape_jit_plan_stats(const ccu_tape* t, int seg_instr, int schedule, ccu_int stats[8]);
 /* Selects the order used by subsequent (re)builds of the specialised kernels and by ccu_tape_get_jit_source. */
 CCU_EXPORT int ccu_tape_set_jit_schedule(ccu_tape* t, int schedule);

@@ -31,6 +31,7 @@ struct ccu_dim3 { unsigned x, y, z; };
 static ccu_dim3 blockIdx, blockDim, threadIdx;
 // staged live-ins (TMA bulk copy -> shared memory on the device) read the scratch slot directly on the host
 static double ccu_host_sm[8192];  // private shared-memory rows: one host "thread" runs at a time
+#define CCU_PF(p)
 #define CCU_SM_DECL
 #define CCU_SM_ST(r, v) ccu_host_sm[r] = (v)
 #define CCU_SM_LD(r) ccu_host_sm[r]
@@ -43,9 +44,13 @@ static double ccu_host_sm[8192];  // private shared-memory rows: one host "threa
 """
 DRIVER = r"""
 extern "C" void run_seg(const ccu::IoDesc* io, long long inst0, long long n_tile, double* sc, long long sstride) {
-  blockDim.x = 1; threadIdx.x = 0;
-  for (long long t = 0; t < n_tile; ++t) { blockIdx.x = (unsigned)t; ccu_seg(*io, inst0, n_tile, sc, sstride); }
+  blockDim.x = CCU_T;
+  for (long long t = 0; t < n_tile; ++t) {
+    blockIdx.x = (unsigned)(t / CCU_T); threadIdx.x = (unsigned)(t % CCU_T);
+    ccu_seg(*io, inst0, n_tile, sc, sstride);
+  }
 }
+extern "C" long long scratch_doubles(long long n_tile) { return (long long)CCU_NSLOTS * CCU_T * ((n_tile + CCU_T - 1) / CCU_T); }
 """
 
 
@@ -65,9 +70,7 @@ def run_sources_on_host(sources, nnz_in, nnz_out, ins, N, null_in=None):
     for j, a in enumerate(outs):
         io.out[j] = a.ctypes.data if a.size else None
         io.out_si[j], io.out_sk[j] = nnz_out[j], 1
-    nslots = max([int(s.split("CCU_ST(")[k].split(",")[0]) for s in sources for k in range(1, len(s.split("CCU_ST(")))
-                  if s.split("CCU_ST(")[k][0].isdigit()] + [0]) + 1
-    scratch = np.full(nslots * N, np.nan)
+    scratch = None
     with tempfile.TemporaryDirectory() as tmp:
         procs = []
         for k, src in enumerate(sources):
@@ -80,6 +83,9 @@ def run_sources_on_host(sources, nnz_in, nnz_out, ins, N, null_in=None):
             assert p.wait() == 0
         for k in range(len(sources)):
             lib = ctypes.CDLL(os.path.join(tmp, "seg%d.so" % k))
+            if scratch is None:  # blocked [CTA][slot][thread] scratch, same size for every segment of a plan
+                lib.scratch_doubles.restype = ctypes.c_longlong
+                scratch = np.full(lib.scratch_doubles(ctypes.c_longlong(N)), np.nan)
             lib.run_seg(ctypes.byref(io), ctypes.c_longlong(0), ctypes.c_longlong(N),
                         scratch.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(N))
     return outs
