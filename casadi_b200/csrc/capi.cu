@@ -226,6 +226,8 @@ void jit_options_from_env(ccu::JitOptions* o) {
   if (const char* p = getenv("CCU_JIT_TILE")) o->tile = atoll(p);
   if (const char* p = getenv("CCU_JIT_STREAMS")) o->streams = atoi(p);
   if (const char* p = getenv("CCU_JIT_PREFETCH")) o->prefetch = atoi(p);
+  if (const char* p = getenv("CCU_JIT_SBLOCK")) o->scratch_block = atoi(p);
+  if (const char* p = getenv("CCU_JIT_RING")) o->ring = atoi(p);
   if (const char* p = getenv("CCU_JIT_STAGE")) o->stage = atoi(p);
   if (const char* p = getenv("CCU_JIT_SPILL")) o->spill = atoi(p);
   if (const char* p = getenv("CCU_JIT_REGVALS")) o->reg_values = atoi(p);
@@ -469,8 +471,8 @@ ccu_int ccu_tape_get_jit_source(const ccu_tape* t, ccu_int segment, char* buf, c
   // generating re-plans the whole tape: keep the sources of the last option set
   char key[160];
   const ccu::JitOptions eff = ccu::jit_resolve(t->jit_opt, t->flops);
-  snprintf(key, sizeof key, "%d,%d,%d,%d,%d,%d,%d,%d,%d", eff.seg_instr, eff.schedule, eff.threads, eff.min_blocks,
-           eff.load_batch, eff.stage, eff.spill, eff.reg_values, eff.prefetch);
+  snprintf(key, sizeof key, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", eff.seg_instr, eff.schedule, eff.threads, eff.min_blocks,
+           eff.load_batch, eff.stage, eff.spill, eff.reg_values, eff.prefetch, eff.scratch_block, eff.ring);
   if (t->jit_src_key != key) {
     std::string err;
     t->jit_src.clear();

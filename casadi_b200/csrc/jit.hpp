@@ -32,9 +32,12 @@ struct JitOptions {
   int threads = 0;        // CTA size; 0 = automatic
   int min_blocks = -1;    // __launch_bounds__ second argument (resident CTAs per SM, bounds the registers); 0 = none, -1 = automatic
   int load_batch = 32;    // cross-segment live-ins read straight from global memory are loaded in groups of this many
+  int scratch_block = 128; // consecutive instances that share a scratch block [block][slot][instance] (capped by the CTA)
+  int ring = -1;          // rows of the cp.async ring that prefetches a segment's live-ins into shared memory (0 = off, -1 = automatic: 40)
   int prefetch = 0;       // 1 / 2: prefetch.global.L2 / .L1 of every live-in (and dense inputs) at kernel entry
   int stage = 0;          // live-ins per segment staged in shared memory by TMA bulk copies: -1 = as many as fit, 0 = off
-  int spill = 0;          // private shared-memory rows for values that do not fit the registers: -1 = what is left, 0 = off
+  int spill = -2;         // private shared-memory rows for values that do not fit the registers: -1 = what is left, 0 = off,
+                          // -2 = automatic: what is left when the launch bounds allow >= 200 registers, else off
   int reg_values = 0;     // doubles planned in registers (0 = from the launch bounds)
   int compile_threads = 0;  // 0 = hardware concurrency (max 32)
   long long tile = 0;     // instances per tile (0 = automatic)

@@ -32,6 +32,11 @@ static ccu_dim3 blockIdx, blockDim, threadIdx;
 // staged live-ins (TMA bulk copy -> shared memory on the device) read the scratch slot directly on the host
 static double ccu_host_sm[8192];  // private shared-memory rows: one host "thread" runs at a time
 #define CCU_PF(p)
+#define CCU_RING_DECL
+#define CCU_RING_ISSUE(row, s)
+#define CCU_RING_COMMIT
+#define CCU_RING_WAIT(n)
+#define CCU_RING_LD(row, s) CCU_LD(s)
 #define CCU_SM_DECL
 #define CCU_SM_ST(r, v) ccu_host_sm[r] = (v)
 #define CCU_SM_LD(r) ccu_host_sm[r]
@@ -50,7 +55,7 @@ extern "C" void run_seg(const ccu::IoDesc* io, long long inst0, long long n_tile
     ccu_seg(*io, inst0, n_tile, sc, sstride);
   }
 }
-extern "C" long long scratch_doubles(long long n_tile) { return (long long)CCU_NSLOTS * CCU_T * ((n_tile + CCU_T - 1) / CCU_T); }
+extern "C" long long scratch_doubles(long long n_tile) { return (long long)CCU_NSLOTS * CCU_T * ((n_tile + CCU_T - 1) / CCU_T); }  // CCU_SB divides CCU_T
 """
 
 
