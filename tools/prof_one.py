@@ -11,7 +11,10 @@ name, sched, seg, threads, minb, N = sys.argv[1], int(sys.argv[2]), int(sys.argv
 reps = int(sys.argv[7]) if len(sys.argv) > 7 else 2
 tape, case = load_tape(name), load_case(name)
 t = CudaTape(tape, mode="interp")
-if seg > 0:
+if seg <= 0:
+    from casadi_b200 import capi
+    t.set_mode(capi.MODE_JIT)  # the automatic plan
+else:
     t.set_jit_schedule(sched)
     t.set_jit_plan(seg, threads, minb, int(os.environ.get("TILE", "0")))
 dev = torch.device("cuda:0")
