@@ -335,7 +335,7 @@ def main_cuda(args):
     roofline = {"bound": "fp64" if t_fp64 >= t_hbm else "hbm", "kernel": kname,
                 "achieved": ach, "peak": p64, "unit": "TFLOP/s", "frac": ach / p64,
                 "peak_source": "FP64 non-FMA issue rate measured live by ccu_fp64_issue_rate (DADD/s); contraction is off by contract",
-                "traffic": NCU_DRAM_BYTES_PER_EVAL if (iJ["mode"] == capi.MODE_JIT and iJ["jit_segments"] == 58) else None,
+                "traffic": NCU_DRAM_BYTES_PER_EVAL if (iJ["mode"] == capi.MODE_JIT and iJ["jit_segments"] in (46, 58)) else None,
                 "traffic_note": "DRAM bytes per evaluation (dram__bytes_read.sum + dram__bytes_write.sum summed over the 58 "
                                 "ccu_seg launches of one tile / instances of the tile) from the ncu capture "
                                 "profiles/r1_launches_jac_bisect_staged_vs_direct.txt (direct column); algorithmic bytes are "

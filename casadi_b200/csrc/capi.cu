@@ -196,8 +196,11 @@ int ensure_scratch(ccu_tape* t) {
 int launch(ccu_tape* t, const ccu::IoDesc& io, long long N, cudaStream_t stream) {
   if (t->mode == CCU_MODE_JIT) {
     const long long tile = ccu::jit_tile_for(t->jit, N, t->sms);
-    if (t->jit.scratch_slots > 0 &&
-        t->scratch.ensure(static_cast<size_t>(t->jit.scratch_slots) * tile * std::max(1, t->jit.streams))) return 1;
+    if (t->jit.chain) {
+      if (t->jit.scratch_slots > 0 &&
+          t->scratch.ensure(static_cast<size_t>(t->jit.scratch_slots) * t->jit.chain_grid * t->jit.threads)) return 1;
+    } else if (t->jit.scratch_slots > 0 &&
+               t->scratch.ensure(static_cast<size_t>(t->jit.scratch_slots) * tile * std::max(1, t->jit.streams))) return 1;
     if (t->ev0) cudaEventRecord(t->ev0, stream);
     long long nl = 0;
     cudaError_t e = ccu::jit_launch(t->jit, io, N, t->scratch.p, tile, stream, &nl);
@@ -228,6 +231,7 @@ void jit_options_from_env(ccu::JitOptions* o) {
   if (const char* p = getenv("CCU_JIT_PREFETCH")) o->prefetch = atoi(p);
   if (const char* p = getenv("CCU_JIT_SBLOCK")) o->scratch_block = atoi(p);
   if (const char* p = getenv("CCU_JIT_RING")) o->ring = atoi(p);
+  if (const char* p = getenv("CCU_JIT_CHAIN")) o->chain = atoi(p);
   if (const char* p = getenv("CCU_JIT_STAGE")) o->stage = atoi(p);
   if (const char* p = getenv("CCU_JIT_SPILL")) o->spill = atoi(p);
   if (const char* p = getenv("CCU_JIT_REGVALS")) o->reg_values = atoi(p);
@@ -245,6 +249,16 @@ int build_jit(ccu_tape* t) {
   if (!ccu::jit_build(t->source(), eff, t->device, &prog, &err)) {
     t->jit_error = err;
     return fail("tape specialisation failed: %s", err.c_str());
+  }
+  if (prog.chain) {
+    // persistent grid = what is resident at once
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(prog.chain), prog.threads,
+                                                                 static_cast<size_t>(prog.chain_smem));
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
+    if (e != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+    prog.chain_grid = per_sm * std::max(sms, 1);
   }
   if (t->jit_built) ccu::jit_destroy(&t->jit);
   t->jit = std::move(prog);
@@ -402,7 +416,8 @@ int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info) {
   info->ctas_per_sm = t->plan.ctas_per_sm;
   info->mode = t->mode;
   if (t->jit_built) {
-    info->jit_segments = static_cast<ccu_int>(t->jit.kernels.size());
+    info->jit_segments = t->jit.segments;
+    info->jit_chained = t->jit.chain ? 1 : 0;
     info->jit_scratch_slots = t->jit.scratch_slots;
     info->jit_tile = t->jit.tile;
     info->jit_compile_ms = static_cast<ccu_int>(t->jit.compile_ms);
@@ -457,6 +472,20 @@ int ccu_tape_jit_plan_stats(const ccu_tape* t, int seg_instr, int schedule, ccu_
   stats[0] = ps.segments; stats[1] = ps.scratch_slots; stats[2] = ps.cross_loads; stats[3] = ps.cross_stores;
   stats[4] = ps.max_segment; stats[5] = static_cast<ccu_int>(ps.schedule_ms); stats[6] = ps.max_live; stats[7] = static_cast<ccu_int>(ps.mean_live);
   return 0;
+}
+
+ccu_int ccu_tape_jit_link_check(const ccu_tape* t) {
+  if (!t) { fail("null tape"); return -1; }
+  const ccu::JitOptions eff = ccu::jit_resolve(t->jit_opt, t->flops);
+  std::vector<std::string> src;
+  std::string err, image;
+  if (!ccu::jit_generate(t->source(), eff, &src, nullptr, &err)) { fail("%s", err.c_str()); return -1; }
+  if (!ccu::jit_link_chain(src, eff, "sm_100a", &image, nullptr, &err)) { fail("%s", err.c_str()); return -1; }
+  return static_cast<ccu_int>(image.size());
+}
+
+const char* ccu_tape_jit_chain_error(const ccu_tape* t) {
+  return (t && t->jit_built) ? t->jit.chain_error.c_str() : "";
 }
 
 int ccu_tape_set_jit_schedule(ccu_tape* t, int schedule) {

@@ -86,6 +86,17 @@ class CudaTape:
         return dict(segments=st[0], scratch_slots=st[1], cross_loads=st[2], cross_stores=st[3], max_segment=st[4],
                     schedule_ms=st[5], max_live=st[6], mean_live=st[7])
 
+    def jit_link_check(self):
+        """Size of the linked persistent-chain cubin of the current plan (host only); raises when NVRTC / nvJitLink
+        cannot produce it."""
+        n = capi.lib().ccu_tape_jit_link_check(self.handle)
+        if n < 0:
+            raise CcuError(capi.last_error())
+        return n
+
+    def jit_chain_error(self):
+        return capi.lib().ccu_tape_jit_chain_error(self.handle).decode()
+
     def jit_sources(self):
         L = capi.lib()
         n = L.ccu_tape_get_jit_source(self.handle, -1, None, 0)

@@ -102,6 +102,7 @@ typedef struct ccu_tape_info {
   ccu_int jit_threads;    /* CTA size of the specialised kernels                                     */
   ccu_int jit_schedule;   /* 0 = reference order, 1 = min-cut bisection order (csrc/tape_schedule.hpp)       */
   ccu_int jit_schedule_ms;/* time spent ordering and cutting the tape                                        */
+  ccu_int jit_chained;    /* 1 = the segments are linked into ONE persistent kernel (one launch per evaluation)*/
 } ccu_tape_info;
 CCU_EXPORT int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info);
 
@@ -132,6 +133,13 @@ CCU_EXPORT ccu_int ccu_tape_get_jit_source(const ccu_tape* t, ccu_int segment, c
  *          largest segment (arithmetic instructions), schedule time in ms,
  *          peak values alive inside one segment (max over segments), the same (mean over segments)}. */
 CCU_EXPORT int ccu_tape_jit_plan_stats(const ccu_tape* t, int seg_instr, int schedule, ccu_int stats[8]);
+/* Compiles the segments of the current plan as relocatable device functions plus the persistent chain kernel and
+ * links them for sm_100a (NVRTC + nvJitLink, both dlopen'ed; works without a GPU).  Returns the size of the linked
+ * cubin in bytes, -1 on failure.  The reference's analogue: the "jit" option compiling the generated C of a whole
+ * Function into one shared object (function_internal.cpp, importer.cpp). */
+CCU_EXPORT ccu_int ccu_tape_jit_link_check(const ccu_tape* t);
+/* Why the built specialisation runs one kernel per segment instead of the chain ("" when chained / not built). */
+CCU_EXPORT const char* ccu_tape_jit_chain_error(const ccu_tape* t);
 /* Selects the order used by subsequent (re)builds of the specialised kernels and by ccu_tape_get_jit_source. */
 CCU_EXPORT int ccu_tape_set_jit_schedule(ccu_tape* t, int schedule);
 

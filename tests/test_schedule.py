@@ -47,8 +47,8 @@ def test_schedule_is_deterministic_and_cached():
 def test_automatic_plan_sizes():
     assert stats("cartpole", 0, 1)["segments"] == 1
     assert stats("quad", 0, 1)["segments"] == 1          # <= 8000 arithmetic instructions: one kernel
-    s = stats("rocket_hess", 0, 1)                        # longer: cut every ~2000
-    assert s["segments"] > 1 and s["max_segment"] <= 2000
+    s = stats("rocket_hess", 0, 1)                        # longer: cut every <= 2500
+    assert s["segments"] > 1 and s["max_segment"] <= 2500
 
 
 @pytest.mark.parametrize("sched", ["0", "1"])
@@ -68,3 +68,20 @@ def test_generated_code_variants_reproduce_reference_bits(sched, opts):
     finally:
         for k in env:
             os.environ.pop(k, None)
+
+
+def test_chain_kernel_links_on_the_host():
+    """The persistent chain kernel (every segment a relocatable device function, linked by nvJitLink for sm_100a)
+    builds without a GPU; skipped when NVRTC / nvJitLink are not loadable."""
+    os.environ["CCU_JIT_SEG"] = "300"
+    try:
+        t = CudaTape(load_tape("quad1_jac"), device=-1)
+        try:
+            n = t.jit_link_check()
+        except Exception as e:  # noqa: BLE001
+            if "not loadable" in str(e):
+                pytest.skip(str(e))
+            raise
+    finally:
+        del os.environ["CCU_JIT_SEG"]
+    assert n > 10000
