@@ -223,6 +223,7 @@ int launch(ccu_tape* t, const ccu::IoDesc& io, long long N, cudaStream_t stream)
 void jit_options_from_env(ccu::JitOptions* o) {
   if (const char* p = getenv("CCU_JIT_SEG")) o->seg_instr = atoi(p);
   if (const char* p = getenv("CCU_JIT_SCHED")) o->schedule = atoi(p);
+  if (const char* p = getenv("CCU_JIT_SEGWEIGHT")) o->seg_weight = atoll(p);
   if (const char* p = getenv("CCU_JIT_THREADS")) o->threads = atoi(p);
   if (const char* p = getenv("CCU_JIT_MINBLOCKS")) o->min_blocks = atoi(p);
   if (const char* p = getenv("CCU_JIT_BATCH")) o->load_batch = atoi(p);
@@ -500,7 +501,7 @@ ccu_int ccu_tape_get_jit_source(const ccu_tape* t, ccu_int segment, char* buf, c
   // generating re-plans the whole tape: keep the sources of the last option set
   char key[160];
   const ccu::JitOptions eff = ccu::jit_resolve(t->jit_opt, t->flops);
-  snprintf(key, sizeof key, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", eff.seg_instr, eff.schedule, eff.threads, eff.min_blocks,
+  snprintf(key, sizeof key, "%lld,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", eff.seg_weight, eff.seg_instr, eff.schedule, eff.threads, eff.min_blocks,
            eff.load_batch, eff.stage, eff.spill, eff.reg_values, eff.prefetch, eff.scratch_block, eff.ring);
   if (t->jit_src_key != key) {
     std::string err;

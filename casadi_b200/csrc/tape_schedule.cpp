@@ -1,6 +1,8 @@
 // Min-cut recursive bisection of the tape's value graph.  See tape_schedule.hpp.
 #include "tape_schedule.hpp"
 
+#include "ccu_isa.h"
+
 #include <algorithm>
 #include <chrono>
 #include <cstdint>
@@ -17,7 +19,25 @@ namespace {
 
 constexpr int kInf = 1 << 28;
 
-struct PieceRec { int begin, end, arith; };
+struct PieceRec { int begin, end, arith; long long weight; };
+
+// estimated SASS instructions of one tape instruction in a specialised kernel (sm_100a, --fmad=false; measured on the
+// quadrotor tapes: division 14, sin/cos 45, everything with a libm slow path is long) -- a kernel has to stay within
+// the instruction cache (a 167 KB primal segment of the Jacobian ran at 14 % issue utilisation, stall_no_instruction
+// 9.2 per issue: profiles/r1_ncu_full_seg_jac_icache.txt)
+int op_weight(const Node& nd) {
+  if (nd.kind == K_OUTPUT) return 3;
+  if (nd.kind != K_ARITH) return 0;
+  switch (nd.dop) {
+    case D_DIV: case D_INV: case D_SQRT: return 14;
+    case D_SIN: case D_COS: return 45;
+    case D_TAN: case D_EXP: case D_LOG: case D_LOG1P: case D_EXPM1: case D_SINH: case D_COSH: case D_TANH: return 50;
+    case D_POW: case D_ATAN2: case D_HYPOT: case D_FMOD: case D_REMAINDER: case D_ASIN: case D_ACOS: case D_ATAN:
+    case D_ASINH: case D_ACOSH: case D_ATANH: case D_ERF: case D_ERFINV: return 90;
+    case D_COPY: return 0;
+    default: return 2;
+  }
+}
 
 // Dinic's maximum flow on a forward-star graph; blocking flows are found iteratively (dependency chains make
 // augmenting paths thousands of edges long).
@@ -231,7 +251,9 @@ struct Bisector {
   void split(std::vector<int>& piece) {
     const int m = static_cast<int>(piece.size());
     const int begin = static_cast<int>(out.size());
-    pieces.push_back({begin, begin + m, arith_count(piece)});
+    long long w = 0;
+    for (int v : piece) w += op_weight(N[v]);
+    pieces.push_back({begin, begin + m, arith_count(piece), w});
     if (m <= std::max(opt.min_piece, 2)) {
       emit(piece);
       return;
@@ -346,16 +368,19 @@ bool schedule_tape(const std::vector<Node>& nodes, const ScheduleOptions& opt, S
   // inside an accepted one starts before that one's end); adjacent small ones are merged
   std::vector<int> merged;
   {
-    std::vector<std::pair<int, int>> segs;  // (begin, arith)
+    const long long wmax = opt.seg_weight > 0 ? opt.seg_weight : (1ll << 60);
+    struct Seg { int begin, arith; long long weight; };
+    std::vector<Seg> segs;
     int covered = 0;
     for (const PieceRec& pc : rec->pieces) {
       if (pc.begin < covered) continue;
-      if (pc.arith <= per || pc.end - pc.begin <= 2) { segs.push_back({pc.begin, pc.arith}); covered = pc.end; }
+      if ((pc.arith <= per && pc.weight <= wmax) || pc.end - pc.begin <= 2) { segs.push_back({pc.begin, pc.arith, pc.weight}); covered = pc.end; }
     }
     int cur = 0;
-    for (const auto& sgm : segs) {
-      if (merged.empty() || cur + sgm.second > per) { merged.push_back(sgm.first); cur = sgm.second; }
-      else cur += sgm.second;
+    long long curw = 0;
+    for (const Seg& sgm : segs) {
+      if (merged.empty() || cur + sgm.arith > per || curw + sgm.weight > wmax) { merged.push_back(sgm.begin); cur = sgm.arith; curw = sgm.weight; }
+      else { cur += sgm.arith; curw += sgm.weight; }
     }
   }
   // constants and inputs go right before their first reader (they are re-materialised by both kernel families)

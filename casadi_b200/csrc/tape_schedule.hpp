@@ -28,6 +28,8 @@ namespace ccu {
 struct ScheduleOptions {
   int method = 1;         // 0 = reference order cut every seg_instr arithmetic instructions; 1 = min-cut bisection
   int seg_instr = 800;    // arithmetic instructions per segment (upper bound for method 1)
+  long long seg_weight = 0;  // upper bound on a segment's estimated SASS instructions (method 1; 0 = none): kernels
+                             // have to fit the instruction cache
   int min_piece = 48;     // pieces of at most this many nodes are not split further
   double pin_frac = 0.1;  // fraction of a piece pinned to either side of a cut
 };

@@ -255,6 +255,41 @@ def test_jit_segmentation_and_tiling_do_not_change_bits(seg, tile):
         assert_bit_equal(x, y, "seg=%d tile=%d out%d" % (seg, tile, j))
 
 
+@pytest.mark.parametrize("env", [
+    {"CCU_JIT_SCHED": "0"},                                                  # the reference's instruction order
+    {"CCU_JIT_RING": "0", "CCU_JIT_SPILL": "0"},                             # plain batched ld.global live-ins
+    {"CCU_JIT_RING": "8", "CCU_JIT_SPILL": "-1", "CCU_JIT_REGVALS": "12"},   # cp.async ring + shared-memory spill rows
+    {"CCU_JIT_STAGE": "-1"},                                                 # TMA bulk staging of the live-ins
+    {"CCU_JIT_PREFETCH": "1", "CCU_JIT_SBLOCK": "32"},                       # L2 prefetch, warp-blocked scratch
+    {"CCU_JIT_CHAIN": "1"},                                                  # all segments linked into one persistent kernel
+    {"CCU_JIT_STREAMS": "3"},                                                # tiles in flight on side streams
+])
+def test_every_specialisation_variant_reproduces_the_reference_bits(env, monkeypatch):
+    """Each code-generation / launch variant of the specialised kernels against the reference goldens: bit-exact on
+    the exact-class tape (rocket hess_lag), and bit-identical to the default plan on a tape with sin/cos."""
+    from util import assert_bit_equal as same
+    base = {}
+    for name in ("rocket_hess", "quad_adj"):
+        tape, case = load_tape(name), load_case(name)
+        base[name] = CudaMap(CudaTape(tape, mode="jit"), case["N"])(case["in"])
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for name in ("rocket_hess", "quad_adj"):
+        tape, case = load_tape(name), load_case(name)
+        t = CudaTape(tape, mode="jit")
+        t.set_jit_plan(seg_instr=700, tile=256 if "CCU_JIT_STREAMS" in env else 0)
+        info = t.info()
+        assert info["jit_segments"] > 3
+        if "CCU_JIT_CHAIN" in env:
+            assert info["jit_chained"] == 1, t.jit_chain_error()
+        got = CudaMap(t, case["N"])(case["in"])
+        for j, (x, y) in enumerate(zip(got, base[name])):
+            same(x, y, "%s %s out%d vs default plan" % (name, env, j))
+        if name == "rocket_hess":
+            for j, (x, y) in enumerate(zip(got, case["out"])):
+                same(x, y[:x.size], "%s %s out%d vs reference" % (name, env, j))
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_host_path_chunked_pipeline_matches_single_chunk(mode, monkeypatch):
     """ccu_map_eval_host cuts the batch into chunks (H2D / compute / D2H overlap); chunking must not change a bit,

@@ -11,8 +11,14 @@ from test_jit_codegen import run_generated
 from util import assert_bit_equal
 
 
-def stats(name, seg, sched):
-    return CudaTape(load_tape(name), device=-1).jit_plan_stats(seg, sched)
+def stats(name, seg, sched, weight=0):
+    """Plan statistics; `weight` = bound on a segment's estimated SASS instructions (0 = none, None = automatic)."""
+    if weight is not None:
+        os.environ["CCU_JIT_SEGWEIGHT"] = str(weight)
+    try:
+        return CudaTape(load_tape(name), device=-1).jit_plan_stats(seg, sched)
+    finally:
+        os.environ.pop("CCU_JIT_SEGWEIGHT", None)
 
 
 @pytest.mark.parametrize("name,seg", [("quad", 800), ("quad", 2000), ("mc", 800), ("rocket_hess", 800), ("quad1_jac", 300)])
@@ -45,9 +51,13 @@ def test_schedule_is_deterministic_and_cached():
 
 
 def test_automatic_plan_sizes():
-    assert stats("cartpole", 0, 1)["segments"] == 1
-    assert stats("quad", 0, 1)["segments"] == 1          # <= 8000 arithmetic instructions: one kernel
-    s = stats("rocket_hess", 0, 1)                        # longer: cut every <= 2500
+    assert stats("cartpole", 0, 1, None)["segments"] == 1
+    # every kernel stays within ~7000 estimated SASS instructions (instruction cache): the 20-step integrator with its
+    # 480 sin/cos and 640 divisions is cut into 9 kernels, ~18 values per cut (reference order at 9 segments: 919 + 741)
+    s = stats("quad", 0, 1, None)
+    assert 4 <= s["segments"] <= 12 and s["cross_loads"] <= 200 and s["cross_stores"] <= 200
+    assert stats("quad", 0, 1, 0)["segments"] == 1        # without that bound: <= 8000 arithmetic instructions, one kernel
+    s = stats("rocket_hess", 0, 1, None)                  # longer: cut every <= 2500
     assert s["segments"] > 1 and s["max_segment"] <= 2500
 
 
