@@ -28,8 +28,9 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = "quadrotor12 RK4x20 multiple-shooting map: F (7197-instr tape) + F.jacobian() (77216-instr tape)"
 HOVER = 1.2 * 9.81 / 4
-# measured with ncu on the Jacobian tape's automatic plan (58 segments): 52.1 KB read + 34.7 KB written per evaluation
-NCU_DRAM_BYTES_PER_EVAL = 86786
+# measured with ncu on the Jacobian tape's automatic plan (41 segments): 39.9 KB read + 31.6 KB written per evaluation
+# (profiles/r1_launches_jac_auto_plan.txt)
+NCU_DRAM_BYTES_PER_EVAL = 71584
 
 
 def parse():
@@ -335,10 +336,10 @@ def main_cuda(args):
     roofline = {"bound": "fp64" if t_fp64 >= t_hbm else "hbm", "kernel": kname,
                 "achieved": ach, "peak": p64, "unit": "TFLOP/s", "frac": ach / p64,
                 "peak_source": "FP64 non-FMA issue rate measured live by ccu_fp64_issue_rate (DADD/s); contraction is off by contract",
-                "traffic": NCU_DRAM_BYTES_PER_EVAL if (iJ["mode"] == capi.MODE_JIT and iJ["jit_segments"] in (46, 58)) else None,
-                "traffic_note": "DRAM bytes per evaluation (dram__bytes_read.sum + dram__bytes_write.sum summed over the 58 "
+                "traffic": NCU_DRAM_BYTES_PER_EVAL if (iJ["mode"] == capi.MODE_JIT and iJ["jit_segments"] == 41) else None,
+                "traffic_note": "DRAM bytes per evaluation (dram__bytes_read.sum + dram__bytes_write.sum summed over the 41 "
                                 "ccu_seg launches of one tile / instances of the tile) from the ncu capture "
-                                "profiles/r1_launches_jac_bisect_staged_vs_direct.txt (direct column); algorithmic bytes are "
+                                "profiles/r1_launches_jac_auto_plan.txt; algorithmic bytes are "
                                 "bytes_per_eval, the rest is the cross-segment work vector (roofline.scratch)",
                 "kernel_ms": jac_ms, "flops_per_eval": flopsJ, "bytes_per_eval": bytesJ,
                 "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
