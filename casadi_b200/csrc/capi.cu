@@ -241,7 +241,8 @@ void jit_options_from_env(ccu::JitOptions* o) {
 // (re)build the specialised kernels with the tape's current jit options
 int build_jit(ccu_tape* t) {
   if (t->device < 0) return fail("tape was compiled without a CUDA device");
-  const ccu::JitOptions eff = ccu::jit_resolve(t->jit_opt, t->flops);
+  const ccu::TapeSource tsrc = t->source();
+  const ccu::JitOptions eff = ccu::jit_resolve(t->jit_opt, t->flops, &tsrc);
   if (eff.threads % 32 != 0 || eff.threads < 32 || eff.threads > 1024)
     return fail("jit: threads must be a multiple of 32 in [32, 1024]");
   CCU_CUDA(cudaSetDevice(t->device));
@@ -466,7 +467,8 @@ int ccu_tape_jit_plan_stats(const ccu_tape* t, int seg_instr, int schedule, ccu_
   ccu::JitOptions o = t->jit_opt;
   if (seg_instr > 0) o.seg_instr = seg_instr;
   if (schedule >= 0) o.schedule = schedule;
-  o = ccu::jit_resolve(o, t->flops);
+  const ccu::TapeSource tsrc = t->source();
+  o = ccu::jit_resolve(o, t->flops, &tsrc);
   ccu::JitPlanStats ps;
   std::string err;
   if (!ccu::jit_plan_stats(t->source(), o, &ps, &err)) return fail("%s", err.c_str());
@@ -477,7 +479,8 @@ int ccu_tape_jit_plan_stats(const ccu_tape* t, int seg_instr, int schedule, ccu_
 
 ccu_int ccu_tape_jit_link_check(const ccu_tape* t) {
   if (!t) { fail("null tape"); return -1; }
-  const ccu::JitOptions eff = ccu::jit_resolve(t->jit_opt, t->flops);
+  const ccu::TapeSource tsrc = t->source();
+  const ccu::JitOptions eff = ccu::jit_resolve(t->jit_opt, t->flops, &tsrc);
   std::vector<std::string> src;
   std::string err, image;
   if (!ccu::jit_generate(t->source(), eff, &src, nullptr, &err)) { fail("%s", err.c_str()); return -1; }
@@ -500,7 +503,8 @@ ccu_int ccu_tape_get_jit_source(const ccu_tape* t, ccu_int segment, char* buf, c
   if (!t) { fail("null tape"); return -1; }
   // generating re-plans the whole tape: keep the sources of the last option set
   char key[160];
-  const ccu::JitOptions eff = ccu::jit_resolve(t->jit_opt, t->flops);
+  const ccu::TapeSource tsrc = t->source();
+  const ccu::JitOptions eff = ccu::jit_resolve(t->jit_opt, t->flops, &tsrc);
   snprintf(key, sizeof key, "%lld,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", eff.seg_weight, eff.seg_instr, eff.schedule, eff.threads, eff.min_blocks,
            eff.load_batch, eff.stage, eff.spill, eff.reg_values, eff.prefetch, eff.scratch_block, eff.ring);
   if (t->jit_src_key != key) {

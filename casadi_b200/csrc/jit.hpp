@@ -78,7 +78,7 @@ struct JitProgram {
 // 8000 arithmetic instructions is ONE kernel with 2 x 256 threads per SM (<= 128 registers; the minimum cuts make
 // its work vector fit); longer tapes are cut every ~2000 instructions and run 2 x 128 threads per SM with up to 255
 // registers, because their segments hold 100-200 values alive at once.
-JitOptions jit_resolve(const JitOptions& opt, long long flops);
+JitOptions jit_resolve(const JitOptions& opt, long long flops, const TapeSource* src = nullptr);
 
 // true when libnvrtc can be loaded in this process
 bool jit_available(std::string* why);
