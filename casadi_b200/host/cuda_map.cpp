@@ -368,23 +368,34 @@ namespace casadi {
   void CudaMap::export_function() {
     builder_ = nullptr;
     has_flag_ = false;
-    if (f_.is_a("SXFunction")) {
-      sx_ = f_;
+    // Nested maps are flattened: Function::map(n, par, max_num_threads) (function.cpp:829-858) builds
+    // f.map(d, "serial").map(T, par), whose memory layout -- T blocks of d consecutive instances -- is exactly that
+    // of f.map(d*T).  Mapping the leaf over d*T device threads keeps the tape short and the parallelism full
+    // (expanding the inner map instead would give T threads a d times longer tape).
+    leaf_ = f_;
+    rep_ = 1;
+    while (leaf_.is_a("Map", true)) {
+      Dict inf = leaf_.info();
+      rep_ *= inf.at("n").to_int();
+      leaf_ = inf.at("f").to_function();
+    }
+    if (leaf_.is_a("SXFunction")) {
+      sx_ = leaf_;
     } else {
       // An MX function whose nodes all have an SX evaluation (mapaccum/fold towers, wrapped maps)
       // collapses to one SX tape ...
       try {
-        sx_ = f_.expand();
+        sx_ = leaf_.expand();
       } catch (std::exception& e) {
         // ... anything else (e.g. a Linsol call, solve_impl.hpp:57-73: "eval_sx not defined") is lowered
         // node by node through the tape builder; unsupported nodes raise from there
-        casadi_assert(f_.is_a("MXFunction"), "Map 'cuda': function '" + f_.name() + "' (" + f_.class_name()
+        casadi_assert(leaf_.is_a("MXFunction"), "Map 'cuda': function '" + leaf_.name() + "' (" + leaf_.class_name()
                       + ") is neither an SX nor an MX function");
         lower_mx();
         return;
       }
     }
-    casadi_assert(!sx_.has_free(), "Map 'cuda': function '" + f_.name() + "' has free variables "
+    casadi_assert(!sx_.has_free(), "Map 'cuda': function '" + leaf_.name() + "' has free variables "
                   + str(sx_.get_free()) + " and cannot be evaluated");
     tape_ = export_tape(sx_);
   }
@@ -392,29 +403,29 @@ namespace casadi {
   void CudaMap::lower_mx() {
     CudaLib& lib = cuda_lib();
     casadi_assert(lib.handle!=nullptr, "Map 'cuda': " + lib.error);
-    casadi_assert(!f_.has_free(), "Map 'cuda': function '" + f_.name() + "' has free variables "
-                  + str(f_.get_free()) + " and cannot be evaluated");
+    casadi_assert(!leaf_.has_free(), "Map 'cuda': function '" + leaf_.name() + "' has free variables "
+                  + str(leaf_.get_free()) + " and cannot be evaluated");
     Lowering L(lib);
     try {
-      std::vector<Vals> in(f_.n_in()), out(f_.n_out());
-      std::vector<const Vals*> a(f_.n_in());
-      std::vector<Vals*> r(f_.n_out());
-      for (casadi_int j=0; j<f_.n_in(); ++j) {
-        in[j].resize(f_.nnz_in(j));
-        for (casadi_int e=0; e<f_.nnz_in(j); ++e) in[j][e] = lib.builder_input(L.b, j, e);
+      std::vector<Vals> in(leaf_.n_in()), out(leaf_.n_out());
+      std::vector<const Vals*> a(leaf_.n_in());
+      std::vector<Vals*> r(leaf_.n_out());
+      for (casadi_int j=0; j<leaf_.n_in(); ++j) {
+        in[j].resize(leaf_.nnz_in(j));
+        for (casadi_int e=0; e<leaf_.nnz_in(j); ++e) in[j][e] = lib.builder_input(L.b, j, e);
         a[j] = &in[j];
       }
-      for (casadi_int j=0; j<f_.n_out(); ++j) {
-        out[j].assign(f_.nnz_out(j), L.cst(0.));
+      for (casadi_int j=0; j<leaf_.n_out(); ++j) {
+        out[j].assign(leaf_.nnz_out(j), L.cst(0.));
         r[j] = &out[j];
       }
-      L.call(f_, a, r);
-      for (casadi_int j=0; j<f_.n_out(); ++j)
-        for (casadi_int e=0; e<f_.nnz_out(j); ++e) lib.builder_output(L.b, j, e, out[j][e]);
+      L.call(leaf_, a, r);
+      for (casadi_int j=0; j<leaf_.n_out(); ++j)
+        for (casadi_int e=0; e<leaf_.nnz_out(j); ++e) lib.builder_output(L.b, j, e, out[j][e]);
       // instances whose QR factorisation is numerically singular make the reference's map fail
       // (LinsolQr::nfact returns 1, linsol_qr.cpp:146-163): counted in one extra, summed output
       if (L.fail_count >= 0) {
-        lib.builder_output(L.b, f_.n_out(), 0, L.fail_count);
+        lib.builder_output(L.b, leaf_.n_out(), 0, L.fail_count);
         has_flag_ = true;
       }
     } catch (...) {
@@ -423,8 +434,8 @@ namespace casadi {
     }
     builder_ = L.b;
     tape_ = Tape();
-    for (casadi_int j=0; j<f_.n_in(); ++j) tape_.nnz_in.push_back(f_.nnz_in(j));
-    for (casadi_int j=0; j<f_.n_out(); ++j) tape_.nnz_out.push_back(f_.nnz_out(j));
+    for (casadi_int j=0; j<leaf_.n_in(); ++j) tape_.nnz_in.push_back(leaf_.nnz_in(j));
+    for (casadi_int j=0; j<leaf_.n_out(); ++j) tape_.nnz_out.push_back(leaf_.nnz_out(j));
     if (has_flag_) tape_.nnz_out.push_back(1);
   }
 
@@ -483,9 +494,9 @@ namespace casadi {
       r.push_back(&n_failed);
       std::vector<int> red(n_out_ + 1, 0);
       red[n_out_] = 1;
-      flag = lib.map_eval_reduce_host(m->tape, n_, arg, get_ptr(r), nullptr, get_ptr(red));
+      flag = lib.map_eval_reduce_host(m->tape, n_*rep_, arg, get_ptr(r), nullptr, get_ptr(red));
     } else {
-      flag = lib.map_eval_host(m->tape, n_, arg, res);
+      flag = lib.map_eval_host(m->tape, n_*rep_, arg, res);
     }
     m->fstats.at("cuda").toc();
     if (!flag && n_failed > 0) {

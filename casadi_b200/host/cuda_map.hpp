@@ -70,6 +70,10 @@ namespace casadi {
   private:
     // The SX function whose tape runs on the device (f_ itself, or f_.expand() for an MX function)
     Function sx_;
+    /** The function one device thread evaluates and how many of its instances one instance of f_ holds: nested
+        maps (Function::map with max_num_threads, function.cpp:829-858) are flattened */
+    Function leaf_;
+    casadi_int rep_;
     Tape tape_;
     int device_;
     // MX functions that cannot be expanded (e.g. Linsol calls) are lowered node by node through the tape

@@ -209,6 +209,20 @@ static void gpu_checks() {
     double rel;
     CHECK(compare(eval(F, in), eval(ref, in), &rel) == 0, "hess_lag must be bit-identical");
   }
+  // ---- thread-capped overload Function::map(n, par, max_num_threads) (function.cpp:829-858): it nests
+  //      f.map(d, "serial").map(T, "cuda"); CudaMap flattens the inner map to d*T device instances
+  {
+    Function c = cartpole(4);
+    for (casadi_int n : {96, 100}) {   // divisible by 8 / not divisible (helper function around the base map)
+      Function ref = c.map(n, "serial"), F = c.map(n, "cuda", 8);
+      auto in = random_inputs(ref, 21, -0.5, 0.5);
+      double rel;
+      compare(eval(F, in), eval(ref, in), &rel);
+      CHECK(rel <= 1e-12, "map(n,'cuda',8) n=" + str(n) + " rel err " + str(rel));
+    }
+    Function nested = c.map(12, "serial").map(8, "cuda");
+    CHECK(nested.class_name() == "CudaMap", nested.class_name());
+  }
   // ---- mapaccum tower (function.py:938-1009): an MXFunction that CudaMap expands to one SX tape
   {
     Function acc = mc_leaf().mapaccum(10);
