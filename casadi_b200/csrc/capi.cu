@@ -233,6 +233,7 @@ void jit_options_from_env(ccu::JitOptions* o) {
   if (const char* p = getenv("CCU_JIT_SBLOCK")) o->scratch_block = atoi(p);
   if (const char* p = getenv("CCU_JIT_RING")) o->ring = atoi(p);
   if (const char* p = getenv("CCU_JIT_CHAIN")) o->chain = atoi(p);
+  if (const char* p = getenv("CCU_JIT_ZIGZAG")) o->zigzag = atoi(p);
   if (const char* p = getenv("CCU_JIT_STAGE")) o->stage = atoi(p);
   if (const char* p = getenv("CCU_JIT_SPILL")) o->spill = atoi(p);
   if (const char* p = getenv("CCU_JIT_REGVALS")) o->reg_values = atoi(p);

@@ -46,6 +46,7 @@ struct JitOptions {
   int compile_threads = 0;  // 0 = hardware concurrency (max 32)
   long long tile = 0;     // instances per tile (0 = automatic)
   int streams = 1;        // tiles in flight at once (each on its own stream and scratch region)
+  int zigzag = 1;         // odd kernels of the chain walk the tile's CTAs in reverse order (L2 reuse across kernels)
   std::string cache_dir;  // compiled cubins are cached here ("" = $CCU_JIT_CACHE or ~/.cache/casadi_cuda)
 };
 
@@ -62,6 +63,7 @@ struct JitProgram {
   int scratch_slots = 0;        // cross-segment values alive at once (per instance)
   long long tile = 0;           // instances per tile (0 = whole batch in one tile)
   int streams = 1;              // tiles in flight at once
+  bool zigzag = true;
   std::vector<cudaStream_t> side;    // created on first use
   std::vector<cudaEvent_t> side_done;
   cudaEvent_t fork = nullptr;

@@ -28,7 +28,7 @@ SHIM = r"""
 #define __launch_bounds__(...)
 static inline double __longlong_as_double(long long x) { double d; std::memcpy(&d, &x, 8); return d; }
 struct ccu_dim3 { unsigned x, y, z; };
-static ccu_dim3 blockIdx, blockDim, threadIdx;
+static ccu_dim3 blockIdx, blockDim, threadIdx, gridDim;
 // staged live-ins (TMA bulk copy -> shared memory on the device) read the scratch slot directly on the host
 static double ccu_host_sm[8192];  // private shared-memory rows: one host "thread" runs at a time
 #define CCU_PF(p)
@@ -48,11 +48,12 @@ static double ccu_host_sm[8192];  // private shared-memory rows: one host "threa
 #define CCU_STAGE_LD(j, s) CCU_LD(s)
 """
 DRIVER = r"""
-extern "C" void run_seg(const ccu::IoDesc* io, long long inst0, long long n_tile, double* sc, long long sstride) {
+extern "C" void run_seg(const ccu::IoDesc* io, long long inst0, long long n_tile, double* sc, long long flip) {
   blockDim.x = CCU_T;
-  for (long long t = 0; t < n_tile; ++t) {
+  gridDim.x = (unsigned)((n_tile + CCU_T - 1) / CCU_T);
+  for (long long t = 0; t < (long long)gridDim.x * CCU_T; ++t) {  // every thread of every CTA, either walking order
     blockIdx.x = (unsigned)(t / CCU_T); threadIdx.x = (unsigned)(t % CCU_T);
-    ccu_seg(*io, inst0, n_tile, sc, sstride);
+    ccu_seg(*io, inst0, n_tile, sc, flip);
   }
 }
 extern "C" long long scratch_doubles(long long n_tile) { return (long long)CCU_NSLOTS * CCU_T * ((n_tile + CCU_T - 1) / CCU_T); }  // CCU_SB divides CCU_T
@@ -92,7 +93,7 @@ def run_sources_on_host(sources, nnz_in, nnz_out, ins, N, null_in=None):
                 lib.scratch_doubles.restype = ctypes.c_longlong
                 scratch = np.full(lib.scratch_doubles(ctypes.c_longlong(N)), np.nan)
             lib.run_seg(ctypes.byref(io), ctypes.c_longlong(0), ctypes.c_longlong(N),
-                        scratch.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(N))
+                        scratch.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(k & 1))  # odd kernels walk in reverse
     return outs
 
 
