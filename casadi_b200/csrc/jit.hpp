@@ -34,6 +34,7 @@ struct JitOptions {
   int min_blocks = -1;    // __launch_bounds__ second argument (resident CTAs per SM, bounds the registers); 0 = none, -1 = automatic
   int load_batch = 32;    // cross-segment live-ins read straight from global memory are loaded in groups of this many
   int scratch_block = 128; // consecutive instances that share a scratch block [block][slot][instance] (capped by the CTA)
+  int ring_inputs = 1;    // inputs go through the ring as well (0 = batched / direct loads)
   int chain = 0;          // persistent chain kernel (all segments linked into one kernel by nvJitLink): 0 = off (default: it
                           // keeps the scratch in L2 but streams 5.7 MB of code per 128 instances through the instruction
                           // cache: 2.1e7 vs 5.8e7 evals/s on the quadrotor Jacobian), -1 = when possible, 1 = required

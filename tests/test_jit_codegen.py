@@ -37,6 +37,8 @@ static double ccu_host_sm[8192];  // private shared-memory rows: one host "threa
 #define CCU_RING_COMMIT
 #define CCU_RING_WAIT(n)
 #define CCU_RING_LD(row, s) CCU_LD(s)
+#define CCU_RING_ISSUE_IN(row, j, k)
+#define CCU_RING_LD_IN(row, j, k) CCU_IN(j, k)
 #define CCU_SM_DECL
 #define CCU_SM_ST(r, v) ccu_host_sm[r] = (v)
 #define CCU_SM_LD(r) ccu_host_sm[r]
