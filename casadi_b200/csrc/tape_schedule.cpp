@@ -314,7 +314,8 @@ bool schedule_tape(const std::vector<Node>& nodes, const ScheduleOptions& opt, S
   const int n = static_cast<int>(nodes.size());
   *S = Schedule();
   const int per = std::max(opt.seg_instr, 16);
-  if (opt.method == 0 || n == 0) {
+  // (the bisection costs seconds per 100 K instructions; very long tapes keep the reference order)
+  if (opt.method == 0 || n == 0 || n > opt.max_nodes) {
     S->order.resize(n);
     for (int k = 0; k < n; ++k) S->order[k] = k;
     S->seg_begin.push_back(0);

@@ -31,6 +31,7 @@ struct ScheduleOptions {
   long long seg_weight = 0;  // upper bound on a segment's estimated SASS instructions (method 1; 0 = none): kernels
                              // have to fit the instruction cache
   int min_piece = 48;     // pieces of at most this many nodes are not split further
+  int max_nodes = 600000; // longer tapes are not re-ordered (method 0)
   double pin_frac = 0.1;  // fraction of a piece pinned to either side of a cut
 };
 
