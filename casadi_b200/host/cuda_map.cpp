@@ -481,20 +481,32 @@ namespace casadi {
   }
 
   int CudaMap::eval(const double** arg, double** res, casadi_int* iw, double* w, void* mem) const {
+    return eval_reduce(arg, res, std::vector<bool>(), std::vector<bool>(), mem);
+  }
+
+  int CudaMap::eval_reduce(const double** arg, double** res, const std::vector<bool>& reduce_in,
+                           const std::vector<bool>& reduce_out, void* mem) const {
     auto m = static_cast<CudaMapMemory*>(mem);
     CudaLib& lib = cuda_lib();
     m->fstats.at("cuda").tic();
     // Same contract as Map::eval_gen (map.cpp:141-157): instance i of input j is arg[j]+i*nnz_in(j);
-    // null arg[j] reads as zero, null res[j] is not computed
+    // null arg[j] reads as zero, null res[j] is not computed.  With reductions (MapSum::eval_gen, mapsum.cpp:154-186):
+    // a reduced input is ONE instance read by all, a reduced output is the sum over the instances.
     int flag;
     double n_failed = 0;
-    if (has_flag_) {
-      // res has sz_res >= n_out + f_.sz_res() entries (Map::init): the scratch tail takes the flag pointer
+    const bool reduced = !reduce_in.empty() || !reduce_out.empty();
+    if (has_flag_ || reduced) {
+      // the failure count of lowered linear solvers is one extra, summed output
       std::vector<double*> r(res, res + n_out_);
-      r.push_back(&n_failed);
-      std::vector<int> red(n_out_ + 1, 0);
-      red[n_out_] = 1;
-      flag = lib.map_eval_reduce_host(m->tape, n_*rep_, arg, get_ptr(r), nullptr, get_ptr(red));
+      std::vector<int> red_out(n_out_, 0), red_in(n_in_, 0);
+      for (size_t j=0; j<reduce_out.size() && j<red_out.size(); ++j) red_out[j] = reduce_out[j];
+      for (size_t j=0; j<reduce_in.size() && j<red_in.size(); ++j) red_in[j] = reduce_in[j];
+      if (has_flag_) {
+        r.push_back(&n_failed);
+        red_out.push_back(1);
+      }
+      flag = lib.map_eval_reduce_host(m->tape, n_*rep_, arg, get_ptr(r), reduce_in.empty() ? nullptr : get_ptr(red_in),
+                                      get_ptr(red_out));
     } else {
       flag = lib.map_eval_host(m->tape, n_*rep_, arg, res);
     }

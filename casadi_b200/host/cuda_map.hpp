@@ -48,6 +48,12 @@ namespace casadi {
     /// Evaluate the function numerically: all n instances on the device
     int eval(const double** arg, double** res, casadi_int* iw, double* w, void* mem) const override;
 
+    /** The same evaluation with MapSum semantics (mapsum.cpp:154-186): reduce_in[j] -- arg[j] is one instance read by
+        every evaluation; reduce_out[j] -- res[j] receives the sum over the instances (fixed-shape tree on the device).
+        Empty vectors = plain map.  Used by CudaMapSum. */
+    int eval_reduce(const double** arg, double** res, const std::vector<bool>& reduce_in,
+                    const std::vector<bool>& reduce_out, void* mem) const;
+
     /// No C code generation for the device path
     bool has_codegen() const override { return false;}
 

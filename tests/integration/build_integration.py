@@ -3,10 +3,10 @@
 
 Runs only where the reference tree and its object files exist (this container: oracle/build_ref.py keeps
 oracle/_ref/obj/*.o).  Steps:
-  1. apply casadi_b200/host/casadi_map_cuda.patch to a scratch copy of casadi/core/map.cpp (under /tmp, removed
-     afterwards -- no reference source is ever written into this repository);
-  2. compile the patched map.cpp and the new casadi_b200/host/cuda_map.cpp with the reference's own flags;
-  3. relink libcasadi.so from the reference objects with map.o replaced and cuda_map.o added
+  1. apply casadi_b200/host/casadi_map_cuda.patch to scratch copies of casadi/core/map.cpp and mapsum.cpp (under /tmp,
+     removed afterwards -- no reference source is ever written into this repository);
+  2. compile the patched files and the new casadi_b200/host/cuda_map.cpp, cuda_mapsum.cpp with the reference's own flags;
+  3. relink libcasadi.so from the reference objects with map.o / mapsum.o replaced and cuda_map.o / cuda_mapsum.o added
      -> tests/integration/_build/lib/ (git-ignored; travels to the GPU box), plugins copied alongside;
   4. build tests/integration/test_cuda_map.cpp against it -> _build/bin/test_cuda_map.
 """
@@ -43,21 +43,28 @@ def build(verbose=True):
            "-I" + os.path.join(build_ref.OUT, "gen", "runtime")]
     base = [build_ref.CXX] + build_ref.FLAGS + build_ref.DEFINES + build_ref.FMI_INC + ["-Dcasadi_EXPORTS"] + inc
     map_o, cm_o = os.path.join(objdir, "map.o"), os.path.join(objdir, "cuda_map.o")
-    if newer(map_o, [patch, os.path.join(ref, "casadi/core/map.cpp"), os.path.join(HOST, "cuda_map.hpp")]):
+    ms_o, cms_o = os.path.join(objdir, "mapsum.o"), os.path.join(objdir, "cuda_mapsum.o")
+    hdrs = [os.path.join(HOST, "cuda_map.hpp"), os.path.join(HOST, "cuda_mapsum.hpp")]
+    if newer(map_o, [patch, os.path.join(ref, "casadi/core/map.cpp")] + hdrs) or \
+            newer(ms_o, [patch, os.path.join(ref, "casadi/core/mapsum.cpp")] + hdrs):
         with tempfile.TemporaryDirectory() as tmp:
             core = os.path.join(tmp, "casadi", "core")
             os.makedirs(core)
-            for f in ("map.cpp", "CMakeLists.txt"):
+            for f in ("map.cpp", "mapsum.cpp", "CMakeLists.txt"):
                 shutil.copy(os.path.join(ref, "casadi", "core", f), core)
             subprocess.check_call(["patch", "-p1", "-s", "-d", tmp, "-i", patch])
             subprocess.check_call(base + ["-c", os.path.join(core, "map.cpp"), "-o", map_o])
-    if newer(cm_o, [os.path.join(HOST, "cuda_map.cpp"), os.path.join(HOST, "cuda_map.hpp")]):
+            subprocess.check_call(base + ["-c", os.path.join(core, "mapsum.cpp"), "-o", ms_o])
+    if newer(cm_o, [os.path.join(HOST, "cuda_map.cpp")] + hdrs):
         subprocess.check_call(base + ["-c", os.path.join(HOST, "cuda_map.cpp"), "-o", cm_o])
+    if newer(cms_o, [os.path.join(HOST, "cuda_mapsum.cpp")] + hdrs):
+        subprocess.check_call(base + ["-c", os.path.join(HOST, "cuda_mapsum.cpp"), "-o", cms_o])
     lib = os.path.join(libdir, "libcasadi.so")
     ref_objs = sorted(os.path.join(build_ref.OUT, "obj", f) for f in os.listdir(os.path.join(build_ref.OUT, "obj"))
-                      if f.endswith(".o") and not f.startswith("plugin_") and f != "map.o")
-    if newer(lib, [map_o, cm_o] + ref_objs):
-        subprocess.check_call([build_ref.CXX, "-shared", "-fopenmp", "-pthread", "-o", lib] + ref_objs + [map_o, cm_o, "-ldl"])
+                      if f.endswith(".o") and not f.startswith("plugin_") and f not in ("map.o", "mapsum.o"))
+    new_objs = [map_o, cm_o, ms_o, cms_o]
+    if newer(lib, new_objs + ref_objs):
+        subprocess.check_call([build_ref.CXX, "-shared", "-fopenmp", "-pthread", "-o", lib] + ref_objs + new_objs + ["-ldl"])
     for p in ("libcasadi_linsol_ldl.so", "libcasadi_linsol_qr.so"):
         src = os.path.join(build_ref.OUT, "lib", p)
         if newer(os.path.join(libdir, p), [src]):

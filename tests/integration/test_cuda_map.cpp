@@ -12,6 +12,7 @@
 #include <unistd.h>
 
 #include "models.hpp"
+#include <casadi/core/mapsum.hpp>  // MapSum::create (internal header of the reference: the class has no public factory with a parallelization argument)
 
 using namespace casadi;
 
@@ -222,6 +223,41 @@ static void gpu_checks() {
     }
     Function nested = c.map(12, "serial").map(8, "cuda");
     CHECK(nested.class_name() == "CudaMap", nested.class_name());
+  }
+  // ---- MapSum with "cuda" (mapsum.cpp:31-54 only knows "serial"): reduced inputs are one instance, reduced outputs
+  //      are summed on the device; derivatives stay on the device (mapsum.cpp:304,367 use parallelization())
+  {
+    casadi_int n = 3000;
+    Function g = mc_leaf();
+    std::vector<bool> rin{false, true}, rout{false, true};
+    Function ref = MapSum::create("ms_ref", "serial", g, n, rin, rout);
+    Function F = MapSum::create("ms_cuda", "cuda", g, n, rin, rout);
+    {  // MapSum::create returns an MX wrapper around the node (wrap_as_needed, mapsum.cpp:50), for "serial" as well
+      bool found = false;
+      for (auto& nm : F.get_function()) found = found || F.get_function(nm).class_name() == "CudaMapSum";
+      CHECK(found, "MapSum::create(..., \"cuda\") must embed a CudaMapSum");
+    }
+    for (casadi_int j = 0; j < F.n_in(); ++j) CHECK(F.sparsity_in(j) == ref.sparsity_in(j), "mapsum sparsity_in");
+    for (casadi_int j = 0; j < F.n_out(); ++j) CHECK(F.sparsity_out(j) == ref.sparsity_out(j), "mapsum sparsity_out");
+    auto in = random_inputs(ref, 31, -1, 1);
+    double rel;
+    auto want = eval(ref, in), got = eval(F, in);
+    std::vector<std::vector<double>> g0{got[0]}, w0{want[0]};
+    compare(g0, w0, &rel);
+    CHECK(rel <= 1e-13, "mapsum: mapped output rel err " + str(rel));    // sin() in the leaf
+    compare(got, want, &rel);
+    CHECK(rel <= 1e-12, "mapsum: summed output rel err " + str(rel));    // tree sum vs sequential sum of 3000 terms
+    Function G = Function::deserialize(F.serialize());
+    {
+      bool found = false;
+      for (auto& nm : G.get_function()) found = found || G.get_function(nm).class_name() == "CudaMapSum";
+      CHECK(found, "deserialized function must embed a CudaMapSum");
+    }
+    CHECK(compare(eval(G, in), got, &rel) == 0, "deserialized mapsum differs");
+    Function dref = ref.forward(1), dF = F.forward(1);
+    auto din = random_inputs(dref, 32, -1, 1);
+    compare(eval(dF, din), eval(dref, din), &rel);
+    CHECK(rel <= 1e-12, "mapsum forward rel err " + str(rel));
   }
   // ---- mapaccum tower (function.py:938-1009): an MXFunction that CudaMap expands to one SX tape
   {
