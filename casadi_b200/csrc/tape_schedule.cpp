@@ -4,6 +4,8 @@
 #include "ccu_isa.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cstdint>
 #include <cstdlib>
@@ -134,21 +136,32 @@ struct FlowNet {
   }
 };
 
+// The recursion is position based so that its two halves can run in parallel: a piece owns the interval
+// [begin, begin + size) of the final order; `lo[v]` is the start of the smallest interval known to contain v.  For a
+// piece [L, H) a node outside it lies entirely before L or at/after H, whatever other threads are refining meanwhile.
 struct Bisector {
   const std::vector<Node>& N;
   const ScheduleOptions& opt;
   int n;
-  std::vector<int> cstart, cons;  // distinct consumers of every arithmetic value
-  std::vector<int> loc;           // node -> index in the current piece (-1 = outside)
-  std::vector<char> done;         // node already placed (belongs to an earlier piece)
-  std::vector<int> ext_z;         // external value -> flow node of the current network (-1 = none, -2 = constant)
-  std::vector<int> ext_touched;
-  std::vector<int> out;           // items in final order
-  std::vector<PieceRec> pieces;   // every piece of the recursion: [begin, end) in `out`, arithmetic instructions
-  FlowNet net;
-  long long cuts = 0;
+  std::vector<int> cstart, cons;      // distinct consumers of every arithmetic value
+  std::vector<std::atomic<int>> lo;   // node -> start of its current interval
+  std::vector<int> out;               // items in final order (written by position)
+  std::vector<PieceRec> pieces;       // every piece of the recursion (any order; sorted at the end)
+  std::mutex pieces_mutex;
+  std::atomic<long long> cuts{0};
+  std::atomic<int> threads_free{0};
 
-  Bisector(const std::vector<Node>& nodes, const ScheduleOptions& o) : N(nodes), opt(o), n(static_cast<int>(nodes.size())) {
+  // per-thread scratch
+  struct Worker {
+    std::vector<int> loc;    // node -> index in the current piece (-1 = outside)
+    std::vector<int> ext_z;  // external value -> flow node of the current network (-1 = none, -2 = constant)
+    std::vector<int> ext_touched;
+    FlowNet net;
+    explicit Worker(int n) : loc(n, -1), ext_z(n, -1) {}
+  };
+
+  Bisector(const std::vector<Node>& nodes, const ScheduleOptions& o)
+      : N(nodes), opt(o), n(static_cast<int>(nodes.size())), lo(nodes.size()) {
     std::vector<int> cnt(n + 1, 0);
     auto each_operand = [&](int k, auto&& f) {
       const Node& nd = N[k];
@@ -161,9 +174,10 @@ struct Bisector {
     cons.resize(cstart[n]);
     std::vector<int> fill(cstart.begin(), cstart.end() - 1);
     for (int k = 0; k < n; ++k) each_operand(k, [&](int u) { cons[fill[u]++] = k; });
-    loc.assign(n, -1);
-    done.assign(n, 0);
-    ext_z.assign(n, -1);
+    for (auto& x : lo) x.store(0, std::memory_order_relaxed);
+    int hw = static_cast<int>(std::thread::hardware_concurrency());
+    if (const char* e = getenv("CCU_SCHED_THREADS")) hw = atoi(e);
+    threads_free = std::max(0, std::min(hw, 16) - 1);
   }
 
   template <class F>
@@ -173,16 +187,20 @@ struct Bisector {
     if (nd.b >= 0 && nd.b != nd.a && N[nd.b].kind == K_ARITH) f(nd.b);
   }
 
-  // minimum cut of `piece` with the first/last npin items of `order` pinned; inD[i] for piece index i.
-  // Of the two extreme minimum cuts (smallest / largest D) the more balanced one is returned.
-  long long mincut(const std::vector<int>& piece, const std::vector<int>& order, int npin, std::vector<char>* inD) {
+  // minimum cut of `piece` = interval [L, H) with the first/last npin items of `order` pinned; inD[i] for piece
+  // index i.  Of the two extreme minimum cuts (smallest / largest D) the more balanced one is returned.
+  long long mincut(Worker& W, const std::vector<int>& piece, const std::vector<int>& order, int npin, int H,
+                   std::vector<char>* inD) {
     const int m = static_cast<int>(piece.size());
     const int S = 0, T = 1;
+    FlowNet& net = W.net;
+    std::vector<int>& loc = W.loc;
+    std::vector<int>& ext_z = W.ext_z;
     net.reset(2 + m);
     auto X = [](int i) { return 2 + i; };
     for (int j = 0; j < npin; ++j) net.add(S, X(loc[order[j]]), kInf);
     for (int j = m - npin; j < m; ++j) net.add(X(loc[order[j]]), T, kInf);
-    ext_touched.clear();
+    W.ext_touched.clear();
     for (int i = 0; i < m; ++i) {
       const int v = piece[i];
       operands(v, [&](int u) {
@@ -196,9 +214,9 @@ struct Bisector {
           bool later = false;
           for (int q = cstart[u]; q < cstart[u + 1]; ++q) {
             const int c = cons[q];
-            if (loc[c] < 0 && !done[c]) { later = true; break; }
+            if (loc[c] < 0 && lo[c].load(std::memory_order_relaxed) >= H) { later = true; break; }
           }
-          ext_touched.push_back(u);
+          W.ext_touched.push_back(u);
           if (later) {
             ext_z[u] = -2;
           } else {
@@ -224,7 +242,7 @@ struct Bisector {
         for (int q = cstart[v]; q < cstart[v + 1]; ++q) net.add(z, X(loc[cons[q]]), kInf);
       }
     }
-    for (int u : ext_touched) ext_z[u] = -1;
+    for (int u : W.ext_touched) ext_z[u] = -1;
     const long long f = net.maxflow(S, T);
     ++cuts;
     std::vector<char> a, b;
@@ -244,20 +262,25 @@ struct Bisector {
     return c;
   }
 
-  void emit(const std::vector<int>& piece) {
-    for (int v : piece) { out.push_back(v); done[v] = 1; }
+  void emit(const std::vector<int>& piece, int L) {
+    for (size_t i = 0; i < piece.size(); ++i) out[L + i] = piece[i];
   }
 
-  void split(std::vector<int>& piece) {
+  // piece occupies [L, L + piece.size()) of the final order
+  void split(Worker& W, std::vector<int>& piece, int L) {
     const int m = static_cast<int>(piece.size());
-    const int begin = static_cast<int>(out.size());
+    const int H = L + m;
     long long w = 0;
     for (int v : piece) w += op_weight(N[v]);
-    pieces.push_back({begin, begin + m, arith_count(piece), w});
+    {
+      std::lock_guard<std::mutex> lock(pieces_mutex);
+      pieces.push_back({L, H, arith_count(piece), w});
+    }
     if (m <= std::max(opt.min_piece, 2)) {
-      emit(piece);
+      emit(piece, L);
       return;
     }
+    std::vector<int>& loc = W.loc;
     for (int i = 0; i < m; ++i) loc[piece[i]] = i;
     const int npin = std::max(1, std::min(m / 2, static_cast<int>(opt.pin_frac * m)));
     // order 1: as inherited; order 2: ASAP levels inside the piece
@@ -275,9 +298,27 @@ struct Bisector {
     std::vector<int> by_level(m);
     for (int i = 0; i < m; ++i) by_level[bucket[lev[i]]++] = piece[i];
     std::vector<char> d1, d2;
-    const long long c1 = mincut(piece, piece, npin, &d1);
-    long long c2 = kInf;
-    if (maxlev > 0) c2 = mincut(piece, by_level, npin, &d2);
+    long long c1 = 0, c2 = kInf;
+    bool both = false;
+    if (maxlev > 0 && m > 4000) {  // the two cuts of a large piece side by side
+      int f = threads_free.load();
+      while (f > 0 && !threads_free.compare_exchange_weak(f, f - 1)) {}
+      if (f > 0) {
+        both = true;
+        std::thread t2([&] {
+          Worker W2(n);
+          for (int i = 0; i < m; ++i) W2.loc[piece[i]] = i;
+          c2 = mincut(W2, piece, by_level, npin, H, &d2);
+          threads_free.fetch_add(1);
+        });
+        c1 = mincut(W, piece, piece, npin, H, &d1);
+        t2.join();
+      }
+    }
+    if (!both) {
+      c1 = mincut(W, piece, piece, npin, H, &d1);
+      if (maxlev > 0) c2 = mincut(W, piece, by_level, npin, H, &d2);
+    }
     auto imbalance = [&](const std::vector<char>& d) {
       int k = 0;
       for (char x : d) k += x;
@@ -290,11 +331,29 @@ struct Bisector {
     for (int i = 0; i < m; ++i) (d[i] ? A : B).push_back(piece[i]);
     std::vector<int>().swap(piece);
     if (A.empty() || B.empty()) {  // cannot happen with pins on both sides; keep the order rather than loop
-      emit(A.empty() ? B : A);
+      emit(A.empty() ? B : A, L);
       return;
     }
-    split(A);
-    split(B);
+    const int mid = L + static_cast<int>(A.size());
+    for (int v : B) lo[v].store(mid, std::memory_order_relaxed);  // (A keeps L)
+    // large halves go to another thread when one is free
+    bool spawned = false;
+    std::thread other;
+    if (static_cast<int>(A.size()) > 2000 && static_cast<int>(B.size()) > 2000) {
+      int f = threads_free.load();
+      while (f > 0 && !threads_free.compare_exchange_weak(f, f - 1)) {}
+      if (f > 0) {
+        spawned = true;
+        other = std::thread([this, &B, mid] {
+          Worker W2(n);
+          split(W2, B, mid);
+          threads_free.fetch_add(1);
+        });
+      }
+    }
+    split(W, A, L);
+    if (spawned) other.join();
+    else split(W, B, mid);
   }
 };
 
@@ -352,13 +411,23 @@ bool schedule_tape(const std::vector<Node>& nodes, const ScheduleOptions& opt, S
     for (int k = 0; k < n; ++k)
       if (nodes[k].kind == K_ARITH || nodes[k].kind == K_OUTPUT) items.push_back(k);
     const size_t n_items = items.size();
-    if (!items.empty()) B.split(items);
-    if (B.out.size() != n_items) { *err = "internal: schedule lost nodes"; return false; }
+    B.out.assign(n_items, -1);
+    if (!items.empty()) {
+      Bisector::Worker W(n);
+      B.split(W, items, 0);
+    }
+    for (int v : B.out)
+      if (v < 0) { *err = "internal: schedule lost nodes"; return false; }
+    // pre-order: by start, enclosing piece first
+    std::sort(B.pieces.begin(), B.pieces.end(), [](const PieceRec& x, const PieceRec& y) {
+      if (x.begin != y.begin) return x.begin < y.begin;
+      return x.end > y.end;
+    });
     auto r = std::make_shared<Recursion>();
     r->n = n;
     r->out = std::move(B.out);
     r->pieces = std::move(B.pieces);
-    r->cuts = B.cuts;
+    r->cuts = B.cuts.load();
     rec = r;
     std::lock_guard<std::mutex> lock(g_cache_mutex);
     g_cache.push_front({key, rec});

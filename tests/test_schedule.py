@@ -95,3 +95,17 @@ def test_chain_kernel_links_on_the_host():
     finally:
         del os.environ["CCU_JIT_SEG"]
     assert n > 10000
+
+
+def test_parallel_recursion_is_deterministic():
+    """The bisection recursion runs its halves (and the two cuts of a large piece) on several threads; the order it
+    produces must not depend on how many."""
+    res = []
+    for th in ("1", "4", "16"):
+        os.environ["CCU_SCHED_THREADS"] = th
+        try:
+            t = CudaTape(load_tape("quad_fwd"), device=-1)
+            res.append(["".join(t.jit_sources())])
+        finally:
+            del os.environ["CCU_SCHED_THREADS"]
+    assert res[0] == res[1] == res[2]
