@@ -29,6 +29,7 @@ namespace ccu {
 struct JitOptions {
   int seg_instr = 0;      // arithmetic instructions per segment; 0 = automatic (jit_resolve)
   long long seg_weight = -1;  // estimated SASS instructions per segment (instruction-cache bound): 0 = none, -1 = automatic
+  int sincos = 1;         // sin(x) and cos(x) of one operand inside a segment become one sincos()
   int interleave = 0;     // > 0: inside a segment, re-order windows of this many instructions level by level (ILP)
   int schedule = 1;       // 0 = reference order, fixed-length segments; 1 = min-cut bisection (tape_schedule.hpp)
   int threads = 0;        // CTA size; 0 = automatic
