@@ -28,9 +28,9 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = "quadrotor12 RK4x20 multiple-shooting map: F (7197-instr tape) + F.jacobian() (77216-instr tape)"
 HOVER = 1.2 * 9.81 / 4
-# measured with ncu on the Jacobian tape's automatic plan (41 segments): 39.9 KB read + 31.6 KB written per evaluation
+# measured with ncu on the Jacobian tape's automatic plan (41 segments): 40.0 KB read + 31.6 KB written per evaluation
 # (profiles/r1_launches_jac_auto_plan.txt)
-NCU_DRAM_BYTES_PER_EVAL = 71584
+NCU_DRAM_BYTES_PER_EVAL = 71569
 
 
 def parse():
