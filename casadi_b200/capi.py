@@ -69,6 +69,7 @@ SYMBOLS = {
     "ccu_tape_last_kernel_ms": (ctypes.c_int, [c_vp, c_d_p]),
     "ccu_launch_count": (c_ll, []),
     "ccu_fp64_issue_rate": (ctypes.c_int, [ctypes.c_int, c_d_p]),
+    "ccu_selftest_fastops": (ctypes.c_int, [ctypes.c_int, c_ll, ctypes.c_ulonglong, ctypes.POINTER(ctypes.c_ulonglong)]),
     "ccu_set_device": (ctypes.c_int, [ctypes.c_int]),
     "ccu_malloc": (c_vp, [c_ll]),
     "ccu_free": (ctypes.c_int, [c_vp]),
@@ -133,3 +134,10 @@ def int_array(vals):
         return None
     a = np.ascontiguousarray([1 if v else 0 for v in vals], np.int32)
     return a
+
+
+def selftest_fastops(n, seed=1, device=0):
+    """(mismatches, flagged, checks) of ccu_selftest_fastops."""
+    c = (ctypes.c_ulonglong * 3)()
+    check(lib().ccu_selftest_fastops(device, n, seed, c))
+    return int(c[0]), int(c[1]), int(c[2])

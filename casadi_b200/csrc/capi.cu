@@ -235,6 +235,7 @@ void jit_options_from_env(ccu::JitOptions* o) {
   if (const char* p = getenv("CCU_JIT_CHAIN")) o->chain = atoi(p);
   if (const char* p = getenv("CCU_JIT_INTERLEAVE")) o->interleave = atoi(p);
   if (const char* p = getenv("CCU_JIT_SINCOS")) o->sincos = atoi(p);
+  if (const char* p = getenv("CCU_JIT_FASTOPS")) o->fastops = atoi(p);
   if (const char* p = getenv("CCU_JIT_RING_INPUTS")) o->ring_inputs = atoi(p);
   if (const char* p = getenv("CCU_JIT_ZIGZAG")) o->zigzag = atoi(p);
   if (const char* p = getenv("CCU_JIT_STAGE")) o->stage = atoi(p);
@@ -509,7 +510,7 @@ ccu_int ccu_tape_get_jit_source(const ccu_tape* t, ccu_int segment, char* buf, c
   char key[160];
   const ccu::TapeSource tsrc = t->source();
   const ccu::JitOptions eff = ccu::jit_resolve(t->jit_opt, t->flops, &tsrc);
-  snprintf(key, sizeof key, "%d,%d,%d,%lld,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", eff.sincos, eff.interleave, eff.ring_inputs, eff.seg_weight, eff.seg_instr, eff.schedule, eff.threads, eff.min_blocks,
+  snprintf(key, sizeof key, "%d,%d,%d,%d,%lld,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", eff.fastops, eff.sincos, eff.interleave, eff.ring_inputs, eff.seg_weight, eff.seg_instr, eff.schedule, eff.threads, eff.min_blocks,
            eff.load_batch, eff.stage, eff.spill, eff.reg_values, eff.prefetch, eff.scratch_block, eff.ring);
   if (t->jit_src_key != key) {
     std::string err;

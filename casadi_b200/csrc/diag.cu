@@ -49,3 +49,107 @@ extern "C" int ccu_fp64_issue_rate(int device, double* ops_per_s) {
   *ops_per_s = static_cast<double>(grid) * block * iters * 8 / (best * 1e-3);
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Fast-path operators of the specialised kernels (ccu_ops.cuh): the divisor-only half of the division on the
+// device (constant divisors are hoisted by the code generator) and a self test against the plain operators.
+#include "ccu_ops.cuh"
+#include "fastops.cuh"
+
+namespace {
+
+__global__ void ccu_div_recip_kernel(const double* c, double* r, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) r[i] = ccu::div_recip(c[i]);
+}
+
+__device__ __forceinline__ unsigned long long ccu_mix(unsigned long long z) {  // splitmix64
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+
+// operand classes: 0 = raw bit patterns (every exponent, nan, inf, denormals), 1 = moderate magnitudes (the regime of
+// the benchmark tapes), 2 = trig arguments up to 2^33 (crosses the fast-path limit), 3 = special values
+__device__ double ccu_operand(unsigned long long h, int cls) {
+  if (cls == 0) return __longlong_as_double(static_cast<long long>(h));
+  if (cls == 1) {
+    const double m = 1.0 + static_cast<double>(h >> 12) * 2.220446049250313e-16;
+    const int e = static_cast<int>((h >> 4) & 63) - 32;
+    return ((h & 1) ? -m : m) * exp2(static_cast<double>(e));
+  }
+  if (cls == 2) {
+    const double m = static_cast<double>(h >> 11) * 1.1102230246251565e-16;
+    return ((h & 1) ? -m : m) * exp2(static_cast<double>((h >> 1) % 34));
+  }
+  const double sp[12] = {0.0, -0.0, 1.0, -1.0, CCU_INF, -CCU_INF, CCU_NAN, 4.9e-324, 2.2250738585072014e-308,
+                         1.7976931348623157e308, 2147483648.0, 3.141592653589793};
+  return sp[h % 12];
+}
+
+__global__ void ccu_fastops_selftest_kernel(long long n, unsigned long long seed, unsigned long long* counts) {
+  unsigned long long mism = 0, flagged = 0, checked = 0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const unsigned long long h0 = ccu_mix(seed + 2 * i), h1 = ccu_mix(seed + 2 * i + 1);
+    const int cls = static_cast<int>(i & 3);
+    const double a = ccu_operand(h0, cls == 2 ? 1 : cls), b = ccu_operand(h1, cls == 2 ? 1 : cls), x = ccu_operand(h0, cls == 1 ? 2 : cls);
+    auto same = [](double u, double v) { return __double_as_longlong(u) == __double_as_longlong(v) || (u != u && v != v); };
+    {  // division, general and with the divisor half hoisted
+      bool bad = false;
+      const double q = ccu::div_fast(a, b, bad);
+      bool bad2 = false;
+      const double q2 = ccu::div_finish(a, b, ccu::div_recip(b), bad2);
+      ++checked;
+      if (bad) ++flagged;
+      else if (!same(q, a / b) || !same(q2, q) || bad2) ++mism;
+    }
+    {  // sincos / sin / cos
+      bool bad = false;
+      double s, c;
+      ccu::sincos_fast(x, &s, &c, bad);
+      const double s1 = ccu::trig_one_fast(x, 0, bad), c1 = ccu::trig_one_fast(x, 1, bad);
+      double sr, cr;
+      sincos(x, &sr, &cr);
+      ++checked;
+      if (bad) ++flagged;
+      else if (!same(s, sr) || !same(c, cr) || !same(s1, sin(x)) || !same(c1, cos(x))) ++mism;
+    }
+  }
+  atomicAdd(&counts[0], mism);
+  atomicAdd(&counts[1], flagged);
+  atomicAdd(&counts[2], checked);
+}
+
+}  // namespace
+
+namespace ccu {
+cudaError_t device_div_recip(const double* c, double* r, int n) {
+  if (n <= 0) return cudaSuccess;
+  double *dc = nullptr, *dr = nullptr;
+  cudaError_t e = cudaMalloc(&dc, sizeof(double) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&dr, sizeof(double) * n);
+  if (e == cudaSuccess) e = cudaMemcpy(dc, c, sizeof(double) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    ccu_div_recip_kernel<<<(n + 127) / 128, 128>>>(dc, dr, n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(r, dr, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  if (dc) cudaFree(dc);
+  if (dr) cudaFree(dr);
+  return e;
+}
+}  // namespace ccu
+
+extern "C" int ccu_selftest_fastops(int device, long long n, unsigned long long seed, unsigned long long counts[3]) {
+  if (!counts || n < 0) return 1;
+  if (cudaSetDevice(device) != cudaSuccess) return 1;
+  unsigned long long* d = nullptr;
+  if (cudaMalloc(&d, 3 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+  cudaMemset(d, 0, 3 * sizeof(unsigned long long));
+  ccu_fastops_selftest_kernel<<<148 * 8, 256>>>(n, seed, d);
+  const cudaError_t e = cudaMemcpy(counts, d, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? 0 : 1;
+}

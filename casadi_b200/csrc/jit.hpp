@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "interp.cuh"
@@ -30,6 +31,10 @@ struct JitOptions {
   int seg_instr = 0;      // arithmetic instructions per segment; 0 = automatic (jit_resolve)
   long long seg_weight = -1;  // estimated SASS instructions per segment (instruction-cache bound): 0 = none, -1 = automatic
   int sincos = 1;         // sin(x) and cos(x) of one operand inside a segment become one sincos()
+  int fastops = 1;        // divisions and sin/cos run on the branch-free fast paths of ccu_ops.cuh; a thread whose operands
+                          // leave their range re-evaluates the segment with the plain operators (bit-identical either way)
+  std::vector<std::pair<double, double>> div_recip;  // (constant divisor, its refined reciprocal as computed on the
+                                                     // device): filled by jit_build, empty = divide in the general form
   int interleave = 0;     // > 0: inside a segment, re-order windows of this many instructions level by level (ILP)
   int schedule = 1;       // 0 = reference order, fixed-length segments; 1 = min-cut bisection (tape_schedule.hpp)
   int threads = 0;        // CTA size; 0 = automatic

@@ -309,10 +309,10 @@ namespace casadi {
   } // namespace
 
   CudaMap::CudaMap(const std::string& name, const Function& f, casadi_int n)
-    : Map(name, f, n), device_(0), builder_(nullptr), has_flag_(false) {
+    : Map(name, f, n), rep_(1), flatten_(true), device_(0), builder_(nullptr), has_flag_(false) {
   }
 
-  CudaMap::CudaMap(DeserializingStream& s) : Map(s), device_(0), builder_(nullptr), has_flag_(false) {
+  CudaMap::CudaMap(DeserializingStream& s) : Map(s), rep_(1), flatten_(true), device_(0), builder_(nullptr), has_flag_(false) {
     // The device program is not serialized (Map::serialize_body packs f_ and n_ only, map.cpp:94-98):
     // it is re-exported from f_, exactly like a freshly created map
     export_function();
@@ -374,7 +374,7 @@ namespace casadi {
     // (expanding the inner map instead would give T threads a d times longer tape).
     leaf_ = f_;
     rep_ = 1;
-    while (leaf_.is_a("Map", true)) {
+    while (flatten_ && leaf_.is_a("Map", true)) {
       Dict inf = leaf_.info();
       rep_ *= inf.at("n").to_int();
       leaf_ = inf.at("f").to_function();
@@ -495,6 +495,8 @@ namespace casadi {
     int flag;
     double n_failed = 0;
     const bool reduced = !reduce_in.empty() || !reduce_out.empty();
+    // reductions are defined over whole instances of f_ (CudaMapSum builds its map with keep_nested())
+    casadi_assert(!reduced || rep_ == 1, "Map 'cuda': reductions over a flattened nested map");
     if (has_flag_ || reduced) {
       // the failure count of lowered linear solvers is one extra, summed output
       std::vector<double*> r(res, res + n_out_);

@@ -70,6 +70,11 @@ namespace casadi {
     };
     static Tape export_tape(const Function& f);
 
+    /** Keep a mapped function that is itself a Map as ONE instance (its inner map is expanded into the tape) instead
+        of flattening it to n*d device instances.  CudaMapSum needs this: a reduced input belongs to a whole
+        instance of f_ and a reduced output is the sum of whole f_ outputs (mapsum.cpp:154-186).  Call before init. */
+    void keep_nested() { flatten_ = false; }
+
   protected:
     explicit CudaMap(DeserializingStream& s);
 
@@ -80,6 +85,7 @@ namespace casadi {
         maps (Function::map with max_num_threads, function.cpp:829-858) are flattened */
     Function leaf_;
     casadi_int rep_;
+    bool flatten_;
     Tape tape_;
     int device_;
     // MX functions that cannot be expanded (e.g. Linsol calls) are lowered node by node through the tape

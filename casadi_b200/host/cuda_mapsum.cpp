@@ -11,9 +11,16 @@ namespace casadi {
     : MapSum(name, f, n, reduce_in, reduce_out) {
   }
 
+  // f_.map(n_, "cuda") without the flattening of nested maps: the reductions act on whole instances of f_
+  static Function make_map(const Function& f, casadi_int n) {
+    CudaMap* cm = new CudaMap("cudamap" + str(n) + "_" + f.name(), f, n);
+    cm->keep_nested();
+    return Function::create(cm, Dict());
+  }
+
   CudaMapSum::CudaMapSum(DeserializingStream& s) : MapSum(s) {
     // the device program is not serialized: it is rebuilt from f_ like for a freshly created object
-    map_ = Map::create("cuda", f_, n_);
+    map_ = make_map(f_, n_);
   }
 
   CudaMapSum::~CudaMapSum() {
@@ -27,7 +34,7 @@ namespace casadi {
   void CudaMapSum::init(const Dict& opts) {
     MapSum::init(opts);
     // Raises here when the function cannot run on the device or no device is present (no CPU fallback)
-    map_ = Map::create("cuda", f_, n_);
+    map_ = make_map(f_, n_);
   }
 
   int CudaMapSum::eval(const double** arg, double** res, casadi_int* iw, double* w, void* mem) const {

@@ -248,6 +248,12 @@ CCU_EXPORT ccu_int ccu_launch_count(void);
 /* Measured FP64 non-FMA issue rate (DADD/s) of `device`: the FP64 denominator of the roofline (SURVEY 8d;
  * contraction is off by contract, so one tape instruction is at best one DADD).  Runs a ~3 ms microbenchmark. */
 CCU_EXPORT int ccu_fp64_issue_rate(int device, double* ops_per_s);
+/* Self test of the branch-free division / sin / cos fast paths the specialised kernels use (csrc/ccu_ops.cuh) against
+ * the plain operators (div.rn.f64, sin, cos, sincos) on `n` generated operand pairs: raw bit patterns, moderate
+ * magnitudes, trig arguments across the 2^31 fast-path limit and special values.  counts[0] = results that differ in
+ * a bit although the fast path did not flag the operands (must be 0), counts[1] = flagged (re-evaluated by the plain
+ * operator in a kernel), counts[2] = checks.  Restates nothing of the reference: parity infrastructure of this library. */
+CCU_EXPORT int ccu_selftest_fastops(int device, long long n, unsigned long long seed, unsigned long long counts[3]);
 
 /* ------------------------------------------------------------------------------------------------
  * Device memory helpers (so a C or C++ host needs no CUDA headers)

@@ -58,7 +58,7 @@ def build_tool(name, extra=()):
     os.makedirs(bindir, exist_ok=True)
     exe = os.path.join(bindir, name)
     src = os.path.join(HERE, name + ".cpp")
-    deps = [src, os.path.join(HERE, "models.hpp")]
+    deps = [src, os.path.join(HERE, "models.hpp"), os.path.join(ROOT, "tools", "bench_models.hpp")]
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
         subprocess.check_call([build_ref.CXX, "-O2"] + build_ref.public_flags() + list(extra) + [
             src, "-o", exe, "-L" + os.path.join(build_ref.OUT, "lib"), "-lcasadi",

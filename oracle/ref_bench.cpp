@@ -43,32 +43,8 @@ static Job make_job(const Function& f, long long n, const std::string& mode, int
   } else {
     j.F = f.map(n, "serial");
   }
-  std::mt19937_64 g(seed);
-  auto u = [&](double a, double b) { return a + (b - a) * std::generate_canonical<double, 53>(g); };
-  const double hover = 1.2 * 9.81 / 4;
-  Sparsity ksp = ccu_models::kkt_sparsity();
-  j.in.resize(f.n_in());
+  ccu_models::bench_inputs(f, n, seed, kind, j.in);
   j.out.resize(f.n_out());
-  for (casadi_int k = 0; k < f.n_in(); ++k) {
-    const long long nz = f.nnz_in(k);
-    j.in[k].resize(n * nz);
-    for (long long i = 0; i < n; ++i) {
-      if (kind == "kkt" && k == 0) {
-        std::vector<double> v = ccu_models::kkt_values(ksp, i);
-        std::copy(v.begin(), v.end(), j.in[k].begin() + i * nz);
-        continue;
-      }
-      for (long long e = 0; e < nz; ++e) {
-        double v;
-        if (kind == "cartpole") v = k == 0 ? u(-0.5, 0.5) : u(-1, 1);
-        else if (kind == "quad") v = k == 0 ? u(-0.3, 0.3) : k == 1 ? hover * (1 + u(-0.1, 0.1)) : u(-1, 1);
-        else if (kind == "rocket") v = k == 0 ? 1.0 + u(-1e-2, 1e-2) + 0.01 * e : k == 1 ? 1.0 * u(0.8, 1.2) : k == 2 ? 1.0 : u(-1, 1);
-        else if (kind == "mc") v = k == 0 ? u(-1, 1) : 0.3 * u(-1.7, 1.7);
-        else v = u(-1, 1);
-        j.in[k][i * nz + e] = v;
-      }
-    }
-  }
   j.arg.assign(j.F.sz_arg(), nullptr);
   j.res.assign(j.F.sz_res(), nullptr);
   j.iw.resize(j.F.sz_iw());
@@ -114,18 +90,12 @@ int main(int argc, char** argv) {
   }
   using namespace ccu_models;
   std::vector<Job> jobs;
-  if (wl == "cartpole") jobs.push_back(make_job(cartpole(4), n, mode, T, 1, "cartpole"));
-  else if (wl == "quad") jobs.push_back(make_job(quadrotor(20), n, mode, T, 2, "quad"));
-  else if (wl == "quad_jac") jobs.push_back(make_job(quadrotor(20).jacobian(), n, mode, T, 2, "quad"));
-  else if (wl == "quad_ms") {
-    Function F = quadrotor(20);
-    jobs.push_back(make_job(F, n, mode, T, 2, "quad"));
-    jobs.push_back(make_job(F.jacobian(), n, mode, T, 2, "quad"));
-  } else if (wl == "rocket_hess") jobs.push_back(make_job(rocket_hess_lag(20), n, mode, T, 3, "rocket"));
-  else if (wl == "mc") jobs.push_back(make_job(mc_rollout(100), n, mode, T, 4, "mc"));
-  else if (wl == "kkt_ldl") jobs.push_back(make_job(kkt_solve("ldl"), n, mode, T, 5, "kkt"));
-  else if (wl == "kkt_qr") jobs.push_back(make_job(kkt_solve("qr"), n, mode, T, 5, "kkt"));
-  else { fprintf(stderr, "unknown workload %s\n", wl.c_str()); return 2; }
+  {
+    std::string kind;
+    std::vector<Function> fs = bench_workload(wl, &kind);
+    const unsigned long long seed = kind == "cartpole" ? 1 : kind == "quad" ? 2 : kind == "rocket" ? 3 : kind == "mc" ? 4 : 5;
+    for (const Function& f : fs) jobs.push_back(make_job(f, n, mode, T, seed, kind));
+  }
 
   std::vector<double> secs;
   for (int r = 0; r < reps + warm; ++r) {

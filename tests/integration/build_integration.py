@@ -71,9 +71,15 @@ def build(verbose=True):
             shutil.copy(src, libdir)
     exe = os.path.join(bindir, "test_cuda_map")
     src = os.path.join(HERE, "test_cuda_map.cpp")
-    if newer(exe, [src, lib, os.path.join(ROOT, "oracle", "models.hpp")]):
+    if newer(exe, [src, lib, os.path.join(ROOT, "tools", "bench_models.hpp")]):
         subprocess.check_call([build_ref.CXX, "-O1", "-g"] + build_ref.public_flags() + ["-I" + os.path.join(ROOT, "oracle"),
                               src, "-o", exe, "-L" + libdir, "-lcasadi", "-Wl,-rpath,$ORIGIN/../lib"])
+    # the plugin benchmark (bench.py's end-to-end leg): same library, the reference's public API only
+    bexe = os.path.join(bindir, "cuda_bench")
+    bsrc = os.path.join(ROOT, "tools", "cuda_bench.cpp")
+    if newer(bexe, [bsrc, lib, os.path.join(ROOT, "tools", "bench_models.hpp")]):
+        subprocess.check_call([build_ref.CXX, "-O2"] + build_ref.public_flags() + ["-I" + os.path.join(ROOT, "tools"),
+                              bsrc, "-o", bexe, "-L" + libdir, "-lcasadi", "-ldl", "-Wl,-rpath,$ORIGIN/../lib"])
     if verbose:
         print("integration build:", exe)
     return exe

@@ -259,6 +259,59 @@ static void gpu_checks() {
     compare(eval(dF, din), eval(dref, din), &rel);
     CHECK(rel <= 1e-12, "mapsum forward rel err " + str(rel));
   }
+  // ---- MapSum("cuda") over a function that is itself a Map: a reduced input is one WHOLE instance of f_ (d inner
+  //      blocks) and a reduced output is the sum of whole f_ outputs (mapsum.cpp:154-186) -- the inner map must not
+  //      be flattened into n*d device instances here
+  {
+    Function g = mc_leaf().map(3, "serial");  // x[4x3], w[2x3] -> xn[4x3], cost[1x3]
+    casadi_int n = 50;
+    std::vector<bool> rin{false, true}, rout{false, true};
+    Function ref = MapSum::create("msn_ref", "serial", g, n, rin, rout);
+    Function F = MapSum::create("msn_cuda", "cuda", g, n, rin, rout);
+    for (casadi_int j = 0; j < F.n_out(); ++j) CHECK(F.sparsity_out(j) == ref.sparsity_out(j), "nested mapsum sparsity_out");
+    auto in = random_inputs(ref, 41, -1, 1);
+    double rel;
+    auto want = eval(ref, in), got = eval(F, in);
+    CHECK(got[1].size() == 3, "nested mapsum: reduced output holds one whole f_ output");
+    compare(got, want, &rel);
+    CHECK(rel <= 1e-12, "mapsum over a nested map rel err " + str(rel));
+  }
+  // ---- second order and Jacobians of the mapped function through the reference API, as checkfunction does
+  //      (test/python/helpers.py:520-688: jacobian, forward-over-reverse, hessian of a scalarised output)
+  {
+    casadi_int n = 4;
+    Function ref = f.map(n, "serial"), F = f.map(n, "cuda");
+    for (int which = 0; which < 3; ++which) {
+      Function dref, dF;
+      std::string what;
+      if (which == 0) { dref = ref.jacobian(); dF = F.jacobian(); what = "jacobian"; }
+      if (which == 1) { dref = ref.reverse(1).forward(2); dF = F.reverse(1).forward(2); what = "forward-over-reverse"; }
+      if (which == 2) { dref = ref.forward(1).reverse(1); dF = F.forward(1).reverse(1); what = "reverse-over-forward"; }
+      for (casadi_int j = 0; j < dF.n_out(); ++j) CHECK(dF.sparsity_out(j) == dref.sparsity_out(j), what + " sparsity_out");
+      auto in = random_inputs(dref, 50 + which, 0.1, 1.0);
+      double rel;
+      compare(eval(dF, in), eval(dref, in), &rel);
+      CHECK(rel <= 1e-12, what + " of the cuda map rel err " + str(rel));
+    }
+    // Hessian of a scalar function of the mapped outputs (MX wrapper calling the map)
+    for (std::string par : {"cuda"}) {
+      std::vector<MX> a;
+      for (casadi_int j = 0; j < ref.n_in(); ++j) a.push_back(MX::sym("a" + str(j), ref.sparsity_in(j)));
+      auto scal = [&](const Function& M) {
+        std::vector<MX> r = M(a);
+        MX s = 0;
+        for (auto& e : r) s += sumsqr(e);
+        MX xv = vec(a[1]);
+        Function S("S", a, {s});
+        return S.factory("H", S.name_in(), {"hess:" + S.name_out(0) + ":" + S.name_in(1) + ":" + S.name_in(1)});
+      };
+      Function Href = scal(ref), Hc = scal(F);
+      auto in = random_inputs(Href, 60, 0.1, 1.0);
+      double rel;
+      compare(eval(Hc, in), eval(Href, in), &rel);
+      CHECK(rel <= 1e-11, "hessian through the cuda map rel err " + str(rel));
+    }
+  }
   // ---- mapaccum tower (function.py:938-1009): an MXFunction that CudaMap expands to one SX tape
   {
     Function acc = mc_leaf().mapaccum(10);

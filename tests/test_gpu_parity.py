@@ -257,6 +257,7 @@ def test_jit_segmentation_and_tiling_do_not_change_bits(seg, tile):
 
 @pytest.mark.parametrize("env", [
     {"CCU_JIT_SCHED": "0"},                                                  # the reference's instruction order
+    {"CCU_JIT_FASTOPS": "0"},                                                # plain div.rn.f64 / sincos() (no speculation)
     {"CCU_JIT_RING": "0", "CCU_JIT_SPILL": "0"},                             # plain batched ld.global live-ins
     {"CCU_JIT_RING": "8", "CCU_JIT_SPILL": "-1", "CCU_JIT_REGVALS": "12"},   # cp.async ring + shared-memory spill rows
     {"CCU_JIT_STAGE": "-1"},                                                 # TMA bulk staging of the live-ins
@@ -312,3 +313,118 @@ def test_host_path_chunked_pipeline_matches_single_chunk(mode, monkeypatch):
     # first period against the reference golden
     err = np.abs(many[1][:P] - case["out"][1]) / np.maximum(np.abs(case["out"][1]), 1.0)
     assert err.max() <= COMPOSITE_RTOL
+
+
+def test_fast_path_operators_match_the_plain_ones_bitwise():
+    """The branch-free division / sin / cos / sincos sequences of the specialised kernels (csrc/ccu_ops.cuh) against
+    div.rn.f64 and the CUDA math library on 2^28 generated operands of four classes (raw bit patterns, moderate
+    magnitudes, trig arguments across the 2^31 fast-path limit, special values): wherever the fast path does not
+    flag its operands the bits must be identical (flagged operands are re-evaluated by the plain operator)."""
+    mism, flagged, checks = capi.selftest_fastops(1 << 28, seed=20261018)
+    assert checks == 2 * (1 << 28)
+    assert mism == 0, "%d of %d fast-path results differ from the plain operators" % (mism, checks)
+    assert 0 < flagged < checks  # the generated operands do exercise the flag (specials, denormals, huge arguments)
+
+
+def test_flagged_threads_re_evaluate_with_the_plain_operators():
+    """Operands outside the fast paths' range (zero and denormal numerators, huge angles, inf, nan) in SOME instances:
+    those threads run their segment a second time on the plain operators; every instance must still match the
+    interpreter kernel (which only uses the plain operators) bit for bit."""
+    tape, case = load_tape("quad"), load_case("quad")
+    N = case["N"]
+    ins = [a.copy() for a in case["in"]]
+    x = ins[0].reshape(N, 12)
+    u = ins[1].reshape(N, 4)
+    x[1::7, :] = 0.0                 # 0 / const: the quotient test of the fast path fails
+    u[2::7, :] = 0.0
+    x[3::7, 6] = 3.0e9               # |angle| >= 2^31: Payne-Hanek reduction
+    x[4::7, 7] = np.inf
+    x[5::7, 9:12] = 1e-310           # denormal rates
+    x[6::11, 8] = np.nan
+    a = CudaMap(tape, N, mode="interp")(ins)
+    b = CudaMap(tape, N, mode="jit")(ins)
+    for j, (p, q) in enumerate(zip(a, b)):
+        assert_bit_equal(p, q, "quad out%d with out-of-range operands: interp vs jit" % j)
+    # untouched instances still reproduce the golden
+    keep = np.ones(N, bool)
+    for r in (1, 2, 3, 4, 5):
+        keep[r::7] = False
+    keep[6::11] = False
+    got = b[0].reshape(N, -1)[keep]
+    want = case["out"][0].reshape(N, -1)[keep]
+    assert (np.abs(got - want) / np.maximum(np.abs(want), 1.0)).max() <= COMPOSITE_RTOL
+
+
+# ---- full-size parity of the multi-segment / multi-tile path (device resident, periodic inputs) ------------------
+def _periodic_device_eval(name, N, mode="jit"):
+    """Evaluates tape `name` for N instances whose inputs repeat the golden case with period P; returns
+    (outputs as torch tensors [nnz, N], P, info)."""
+    import torch
+    tape, case = load_tape(name), load_case(name)
+    t = CudaTape(tape, mode=mode)
+    dev = torch.device("cuda:0")
+    P = case["N"]
+    reps = (N + P - 1) // P
+    d_in = []
+    for a, n in zip(case["in"], t.nnz_in):
+        x = torch.from_numpy(a.reshape(P, n)).t().contiguous().to(dev)
+        d_in.append(x.repeat(1, reps)[:, :N].contiguous() if n else x)
+    d_out = [torch.empty((n, N), dtype=torch.float64, device=dev) for n in t.nnz_out]
+    t.eval_device(N, [x.data_ptr() if x.numel() else None for x in d_in], [x.data_ptr() for x in d_out],
+                  layout=LAYOUT_SOA, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return d_out, P, case, t.info()
+
+
+def _assert_every_period_equals_the_first(d_out, P, N, what):
+    import torch
+    full = N // P
+    for j, o in enumerate(d_out):
+        bits = o.view(torch.int64)
+        first = bits[:, :P]
+        body = bits[:, :full * P].reshape(bits.shape[0], full, P)
+        bad = (body != first[:, None, :]).any(dim=2).any(dim=0)  # per period
+        assert not bool(bad.any()), "%s out%d: period(s) %s differ from period 0" % (
+            what, j, torch.nonzero(bad).flatten()[:8].tolist())
+        if N > full * P:
+            tail = bits[:, full * P:]
+            assert bool((tail == first[:, :tail.shape[1]]).all()), "%s out%d: ragged tail differs" % (what, j)
+
+
+@pytest.mark.parametrize("name,N,exact", [
+    ("quad_jac", 1600000 + 77, False),   # 41 segments, 753 scratch slots, >= 2 automatic tiles, ragged last CTA
+    ("rocket_hess", 1000000, True),      # BASELINE config 2 at its stated size
+    ("quad_adj", 1000003, False),
+    ("mc", 10000000, False),             # BASELINE config 3 chunk size (1e7 samples)
+])
+def test_full_size_multi_tile_parity(name, N, exact):
+    """BASELINE-size batches through the specialised kernels: every tile, every CTA and the ragged tail must produce
+    the bits of period 0, and period 0 must be the reference golden (bit-exact for the exact-class tape; within the
+    composite tolerance where sin/cos are chained into arithmetic)."""
+    d_out, P, case, info = _periodic_device_eval(name, N)
+    assert info["mode"] == capi.MODE_JIT
+    if name == "quad_jac":
+        assert info["jit_segments"] > 10 and info["jit_scratch_slots"] > 100
+    _assert_every_period_equals_the_first(d_out, P, N, name)
+    for j, o in enumerate(d_out):
+        got = o[:, :P].t().contiguous().cpu().numpy().ravel()
+        want = case["out"][j]
+        if exact:
+            assert_bit_equal(got, want, "%s out%d period 0 vs reference" % (name, j))
+        else:
+            err = np.abs(got - want) / np.maximum(np.abs(want), 1.0)
+            assert err.max() <= COMPOSITE_RTOL, (name, j, err.max())
+            print("%s out%d: worst distance to the reference %g ulp" % (name, j, float(ulp_diff(got, want).max())))
+
+
+def test_full_size_interpreter_matches_specialised_kernels_on_every_tile():
+    """The interpreter kernel at 1e6 instances of a spilling tape (global scratch per CTA) against the specialised
+    kernels: identical bits everywhere."""
+    import torch
+    N = 1000000
+    a, P, _, ia = _periodic_device_eval("quad", N, mode="interp")
+    b, _, _, ib = _periodic_device_eval("quad", N, mode="jit")
+    assert ia["mode"] == capi.MODE_INTERP and ib["mode"] == capi.MODE_JIT
+    for j, (x, y) in enumerate(zip(a, b)):
+        assert bool((x.view(torch.int64) == y.view(torch.int64)).all()), "quad out%d interp vs jit at N=1e6" % j
+    _assert_every_period_equals_the_first(a, P, N, "quad (interp)")

@@ -31,7 +31,9 @@ struct ccu_dim3 { unsigned x, y, z; };
 static ccu_dim3 blockIdx, blockDim, threadIdx, gridDim;
 // staged live-ins (TMA bulk copy -> shared memory on the device) read the scratch slot directly on the host
 static double ccu_host_sm[8192];  // private shared-memory rows: one host "thread" runs at a time
+#define CCU_HOST_BUILD 1
 #define CCU_PF(p)
+#define CCU_RING_DRAIN
 #define CCU_RING_DECL
 #define CCU_RING_ISSUE(row, s)
 #define CCU_RING_COMMIT
