@@ -67,6 +67,7 @@ SYMBOLS = {
     "ccu_linsol_solve_host": (ctypes.c_int, [c_vp, c_ll, c_d_p, c_d_p, c_d_p, c_ll_p]),
     "ccu_linsol_solve_device": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]),
     "ccu_tape_last_kernel_ms": (ctypes.c_int, [c_vp, c_d_p]),
+    "ccu_tape_last_eval_stats": (ctypes.c_int, [c_vp, c_d_p]),
     "ccu_launch_count": (c_ll, []),
     "ccu_fp64_issue_rate": (ctypes.c_int, [ctypes.c_int, c_d_p]),
     "ccu_selftest_fastops": (ctypes.c_int, [ctypes.c_int, c_ll, ctypes.c_ulonglong, ctypes.POINTER(ctypes.c_ulonglong)]),

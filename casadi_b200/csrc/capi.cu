@@ -7,11 +7,15 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ccu_isa.h"
@@ -65,6 +69,92 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// page-locked host staging buffer
+struct PinBuf {
+  double* p = nullptr;
+  size_t cap = 0;  // doubles
+  int ensure(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaHostAlloc(&p, n * sizeof(double), cudaHostAllocDefault);
+    if (e != cudaSuccess) { p = nullptr; return fail("cudaHostAlloc of %zu bytes failed: %s", n * sizeof(double), cudaGetErrorString(e)); }
+    cap = n;
+    return 0;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// Multi-threaded memcpy between the caller's pageable buffers and the pinned staging of the host path: one thread
+// moves ~10 GB/s, the PCIe link 55 GB/s, so the copies of a chunk are cut into slices taken by a few persistent
+// workers (CCU_HOST_THREADS, default min(8, cores/2)) and the calling thread.
+class CopyPool {
+ public:
+  static CopyPool& get() { static CopyPool pool; return pool; }
+  void copy(void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return;
+    const size_t kSlice = 2u << 20;
+    if (workers_.empty() || bytes <= kSlice) { std::memcpy(dst, src, bytes); return; }
+    std::lock_guard<std::mutex> one(run_mu_);  // one copy at a time
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      dst_ = static_cast<char*>(dst); src_ = static_cast<const char*>(src); bytes_ = bytes;
+      slices_ = (bytes + kSlice - 1) / kSlice;
+      next_.store(0); done_.store(0);
+      ++epoch_;
+    }
+    cv_.notify_all();
+    work(kSlice);
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return done_.load() == slices_; });
+  }
+  int threads() const { return static_cast<int>(workers_.size()) + 1; }
+
+ private:
+  CopyPool() {
+    int n = static_cast<int>(std::thread::hardware_concurrency()) / 2;
+    n = std::max(1, std::min(8, n));
+    if (const char* e = getenv("CCU_HOST_THREADS")) n = std::max(1, atoi(e));
+    for (int i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
+    for (auto& t : workers_) t.detach();  // workers live as long as the process
+  }
+  void work(size_t slice) {
+    for (;;) {
+      const size_t k = next_.fetch_add(1);
+      if (k >= slices_) return;
+      const size_t off = k * slice, len = std::min(slice, bytes_ - off);
+      std::memcpy(dst_ + off, src_ + off, len);
+      if (done_.fetch_add(1) + 1 == slices_) { std::lock_guard<std::mutex> lk(mu_); cv_done_.notify_all(); }
+    }
+  }
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return epoch_ != seen; });
+        seen = epoch_;
+      }
+      work(2u << 20);
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, cv_done_;
+  char* dst_ = nullptr;
+  const char* src_ = nullptr;
+  size_t bytes_ = 0, slices_ = 0;
+  std::atomic<size_t> next_{0}, done_{0};
+  unsigned long long epoch_ = 0;
+};
+
+// true when the driver can DMA from / to `p` directly (page-locked or managed memory)
+bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
 // staging of the host-pointer path (eval_host_impl): [slot] double buffering
 struct HostPipe {
   bool ready = false;
@@ -73,11 +163,20 @@ struct HostPipe {
   std::vector<DevBuf> in_aos[2], in_soa[2], out_aos[2], out_soa[2];
   std::vector<DevBuf> bcast;  // reduce_in operands (one instance)
   DevBuf red;
+  // pageable caller buffers go through pinned staging (the DMA engines cannot read pageable memory; the driver's own
+  // staging of cudaMemcpyAsync is synchronous and serialises the pipeline)
+  std::vector<PinBuf> in_pin[2], out_pin[2];
+  PinBuf red_pin;
+  cudaEvent_t tev[2][6] = {};  // per slot: start/stop of the H2D, compute and D2H phase (timing enabled)
+  bool tev_used[2] = {false, false};
   void release() {
     for (int b = 0; b < 2; ++b) {
       for (auto* v : {&in_aos[b], &in_soa[b], &out_aos[b], &out_soa[b]}) for (auto& x : *v) x.release();
+      for (auto* v : {&in_pin[b], &out_pin[b]}) for (auto& x : *v) x.release();
       for (int k = 0; k < 3; ++k) if (ev[b][k]) cudaEventDestroy(ev[b][k]);
+      for (int k = 0; k < 6; ++k) if (tev[b][k]) cudaEventDestroy(tev[b][k]);
     }
+    red_pin.release();
     for (auto& x : bcast) x.release();
     red.release();
     for (int k = 0; k < 3; ++k) if (s[k]) cudaStreamDestroy(s[k]);
@@ -109,6 +208,9 @@ struct ccu_tape {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
+  // last host-pointer evaluation: device time of the three pipeline phases (summed over the chunks; they overlap),
+  // time the calling thread spent copying between pageable memory and the pinned staging, wall time, staged bytes
+  double st_h2d_ms = 0, st_kernel_ms = 0, st_d2h_ms = 0, st_stage_ms = 0, st_wall_ms = 0, st_staged_bytes = 0;
   // specialised kernels (jit.hpp); mode: CCU_MODE_INTERP or CCU_MODE_JIT
   int mode = CCU_MODE_INTERP;
   ccu::JitOptions jit_opt;
@@ -632,27 +734,18 @@ int ccu_reduce_tree_device(int device, double* d_part, ccu_int N_global, ccu_int
 }
 
 // Host-pointer evaluation (what CudaMap::eval calls): the batch is cut into chunks that flow through a
-// three-stage pipeline on three streams with double-buffered device staging,
-//     H2D (AoS)  ->  [AoS->SoA, tape kernels on SoA, SoA->AoS | block sums]  ->  D2H (AoS)
+// pipeline on three streams with double-buffered device staging,
+//     [pageable -> pinned]  H2D (AoS)  ->  [AoS->SoA, tape kernels on SoA, SoA->AoS | block sums]  ->  D2H (AoS)  [pinned -> pageable]
 // so the PCIe transfers of chunk c+1 / c-1 overlap the kernels of chunk c, and the tape kernels always run
-// on the coalesced SoA layout.  Chunks are multiples of kReduceBlock, so reduce_out block sums land at their
-// global positions and the summation tree is the same as for a single launch.
-static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res,
-                          const int* reduce_in, const int* reduce_out) {
-  if (check_eval_args(t, N)) return 1;
-  CCU_CUDA(cudaSetDevice(t->device));
+// on the coalesced SoA layout.  Caller buffers that are not page-locked (what a CasADi caller normally owns:
+// std::vector / DM storage) are copied through pinned staging by the calling thread and the CopyPool workers while
+// the device works on the neighbouring chunks; page-locked buffers are used directly.  Chunks are multiples of
+// kReduceBlock, so reduce_out block sums land at their global positions and the summation tree is the same as for a
+// single launch.
+static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res,
+                            const int* reduce_in, const int* reduce_out) {
   const size_t n_in = t->nnz_in.size(), n_out = t->nnz_out.size();
   HostPipe& hp = t->pipe;
-  if (!hp.ready) {
-    for (int k = 0; k < 3; ++k) CCU_CUDA(cudaStreamCreateWithFlags(&hp.s[k], cudaStreamNonBlocking));
-    for (int b = 0; b < 2; ++b)
-      for (int k = 0; k < 3; ++k) CCU_CUDA(cudaEventCreateWithFlags(&hp.ev[b][k], cudaEventDisableTiming));
-    for (int b = 0; b < 2; ++b) {
-      hp.in_aos[b].resize(n_in); hp.in_soa[b].resize(n_in); hp.out_aos[b].resize(n_out); hp.out_soa[b].resize(n_out);
-    }
-    hp.bcast.resize(n_in);
-    hp.ready = true;
-  }
   cudaStream_t s_h2d = hp.s[0], s_cmp = hp.s[1], s_d2h = hp.s[2];
   // chunk size: a multiple of kReduceBlock; ~8 chunks per call, between 64Ki and 1Mi instances
   long long C = (N + 7) / 8;
@@ -663,6 +756,17 @@ static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, doub
   const long long nblocks = (N + ccu::kReduceBlock - 1) / ccu::kReduceBlock;
   auto is_rin = [&](size_t j) { return reduce_in && reduce_in[j]; };
   auto is_rout = [&](size_t j) { return reduce_out && reduce_out[j]; };
+  // which caller buffers need pinned staging
+  std::vector<char> stage_in(n_in, 0), stage_out(n_out, 0);
+  const char* force = getenv("CCU_HOST_STAGING");  // "0": never stage (driver-staged copies), "1": always
+  for (size_t j = 0; j < n_in; ++j)
+    if (arg[j] && t->nnz_in[j] > 0 && !is_rin(j)) stage_in[j] = force ? force[0] == '1' : !host_ptr_is_pinned(arg[j]);
+  for (size_t j = 0; j < n_out; ++j)
+    if (res[j] && t->nnz_out[j] > 0 && !is_rout(j)) stage_out[j] = force ? force[0] == '1' : !host_ptr_is_pinned(res[j]);
+  auto stage_ms = [&](const std::chrono::steady_clock::time_point& t0) {
+    t->st_stage_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  };
+  CopyPool& pool = CopyPool::get();
   // broadcast (reduce_in) inputs: one instance, copied once
   for (size_t j = 0; j < n_in; ++j) {
     if (!is_rin(j) || !arg[j] || t->nnz_in[j] == 0) continue;
@@ -673,27 +777,76 @@ static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, doub
     if (!is_rout(j) || !res[j] || t->nnz_out[j] == 0) continue;
     if (t->d_part[j].ensure(static_cast<size_t>(std::max<long long>(nblocks, 1)) * t->nnz_out[j])) return 1;
   }
-  int rc = 0;
-  for (long long c = 0; c < nchunks && rc == 0; ++c) {
+  // accumulate the phase times of the chunk that used slot b last
+  auto harvest = [&](int b) {
+    if (!hp.tev_used[b]) return;
+    float f = 0;
+    if (cudaEventSynchronize(hp.tev[b][5]) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaEventElapsedTime(&f, hp.tev[b][0], hp.tev[b][1]) == cudaSuccess) t->st_h2d_ms += f;
+    if (cudaEventElapsedTime(&f, hp.tev[b][2], hp.tev[b][3]) == cudaSuccess) t->st_kernel_ms += f;
+    if (cudaEventElapsedTime(&f, hp.tev[b][4], hp.tev[b][5]) == cudaSuccess) t->st_d2h_ms += f;
+    cudaGetLastError();
+    hp.tev_used[b] = false;
+  };
+  // copy the results of chunk c out of the pinned staging of its slot (after its D2H has completed)
+  auto copy_out = [&](long long c) -> int {
+    const int b = static_cast<int>(c & 1);
+    const long long i0 = c * C, n = std::min(C, N - i0);
+    bool any = false;
+    for (size_t j = 0; j < n_out; ++j) any = any || stage_out[j];
+    if (!any) return 0;
+    CCU_CUDA(cudaEventSynchronize(hp.ev[b][2]));
+    const auto t0 = std::chrono::steady_clock::now();
+    for (size_t j = 0; j < n_out; ++j) {
+      if (!stage_out[j]) continue;
+      const size_t bytes = static_cast<size_t>(n) * t->nnz_out[j] * 8;
+      pool.copy(res[j] + i0 * t->nnz_out[j], hp.out_pin[b][j].p, bytes);
+      t->st_staged_bytes += static_cast<double>(bytes);
+    }
+    stage_ms(t0);
+    return 0;
+  };
+  for (long long c = 0; c < nchunks; ++c) {
     const int b = static_cast<int>(c & 1);
     const long long i0 = c * C, n = std::min(C, N - i0);
     std::vector<const double*> d_arg(n_in, nullptr);
     std::vector<double*> d_res(n_out, nullptr);
-    // ---- stage 1: H2D (the staging of slot b is free once chunk c-2 has been computed)
+    harvest(b);
+    // ---- stage 0 (host): pageable inputs of chunk c -> pinned staging of slot b (free once the H2D of chunk c-2 is done)
+    {
+      bool any = false;
+      for (size_t j = 0; j < n_in; ++j) any = any || stage_in[j];
+      if (any) {
+        if (c >= 2) CCU_CUDA(cudaEventSynchronize(hp.ev[b][0]));
+        const auto t0 = std::chrono::steady_clock::now();
+        for (size_t j = 0; j < n_in; ++j) {
+          if (!stage_in[j]) continue;
+          if (hp.in_pin[b][j].ensure(static_cast<size_t>(t->nnz_in[j]) * C)) return 1;
+          const size_t bytes = static_cast<size_t>(n) * t->nnz_in[j] * 8;
+          pool.copy(hp.in_pin[b][j].p, arg[j] + i0 * t->nnz_in[j], bytes);
+          t->st_staged_bytes += static_cast<double>(bytes);
+        }
+        stage_ms(t0);
+      }
+    }
+    // ---- stage 1: H2D (the device staging of slot b is free once chunk c-2 has been computed)
     CCU_CUDA(cudaStreamWaitEvent(s_h2d, hp.ev[b][1], 0));
+    CCU_CUDA(cudaEventRecord(hp.tev[b][0], s_h2d));
     for (size_t j = 0; j < n_in; ++j) {
       if (!arg[j] || t->nnz_in[j] == 0) continue;
       if (is_rin(j)) { d_arg[j] = hp.bcast[j].p; continue; }
       const size_t cnt = static_cast<size_t>(t->nnz_in[j]) * C;
       if (hp.in_aos[b][j].ensure(cnt) || hp.in_soa[b][j].ensure(cnt)) return 1;
-      CCU_CUDA(cudaMemcpyAsync(hp.in_aos[b][j].p, arg[j] + i0 * t->nnz_in[j], static_cast<size_t>(n) * t->nnz_in[j] * 8,
-                               cudaMemcpyHostToDevice, s_h2d));
+      const double* src = stage_in[j] ? hp.in_pin[b][j].p : arg[j] + i0 * t->nnz_in[j];
+      CCU_CUDA(cudaMemcpyAsync(hp.in_aos[b][j].p, src, static_cast<size_t>(n) * t->nnz_in[j] * 8, cudaMemcpyHostToDevice, s_h2d));
       d_arg[j] = hp.in_soa[b][j].p;
     }
+    CCU_CUDA(cudaEventRecord(hp.tev[b][1], s_h2d));
     CCU_CUDA(cudaEventRecord(hp.ev[b][0], s_h2d));
     // ---- stage 2: compute (the output staging of slot b is free once chunk c-2 has been copied back)
     CCU_CUDA(cudaStreamWaitEvent(s_cmp, hp.ev[b][0], 0));
     CCU_CUDA(cudaStreamWaitEvent(s_cmp, hp.ev[b][2], 0));
+    CCU_CUDA(cudaEventRecord(hp.tev[b][2], s_cmp));
     for (size_t j = 0; j < n_in; ++j) {
       if (!arg[j] || t->nnz_in[j] == 0 || is_rin(j)) continue;
       CCU_CUDA(ccu::launch_aos_to_soa(hp.in_aos[b][j].p, hp.in_soa[b][j].p, n, static_cast<int>(t->nnz_in[j]), n, s_cmp));
@@ -704,6 +857,7 @@ static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, doub
       const size_t cnt = static_cast<size_t>(t->nnz_out[j]) * C;
       if (hp.out_soa[b][j].ensure(cnt)) return 1;
       if (!is_rout(j) && hp.out_aos[b][j].ensure(cnt)) return 1;
+      if (stage_out[j] && hp.out_pin[b][j].ensure(cnt)) return 1;
       d_res[j] = hp.out_soa[b][j].p;
     }
     ccu::IoDesc io;
@@ -719,29 +873,70 @@ static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, doub
       }
       g_launches++;
     }
+    CCU_CUDA(cudaEventRecord(hp.tev[b][3], s_cmp));
     CCU_CUDA(cudaEventRecord(hp.ev[b][1], s_cmp));
     // ---- stage 3: D2H
     CCU_CUDA(cudaStreamWaitEvent(s_d2h, hp.ev[b][1], 0));
+    CCU_CUDA(cudaEventRecord(hp.tev[b][4], s_d2h));
     for (size_t j = 0; j < n_out; ++j) {
       if (!d_res[j] || is_rout(j)) continue;
-      CCU_CUDA(cudaMemcpyAsync(res[j] + i0 * t->nnz_out[j], hp.out_aos[b][j].p, static_cast<size_t>(n) * t->nnz_out[j] * 8,
-                               cudaMemcpyDeviceToHost, s_d2h));
+      double* dst = stage_out[j] ? hp.out_pin[b][j].p : res[j] + i0 * t->nnz_out[j];
+      CCU_CUDA(cudaMemcpyAsync(dst, hp.out_aos[b][j].p, static_cast<size_t>(n) * t->nnz_out[j] * 8, cudaMemcpyDeviceToHost, s_d2h));
     }
+    CCU_CUDA(cudaEventRecord(hp.tev[b][5], s_d2h));
     CCU_CUDA(cudaEventRecord(hp.ev[b][2], s_d2h));
+    hp.tev_used[b] = true;
+    // ---- stage 4 (host): results of chunk c-1, pinned staging -> caller memory, while the device works on chunk c
+    if (c > 0 && copy_out(c - 1)) return 1;
   }
+  if (nchunks > 0 && copy_out(nchunks - 1)) return 1;
   // reduced outputs: level-1 tree over the block sums, then a tiny D2H
-  for (size_t j = 0; j < n_out && rc == 0; ++j) {
+  for (size_t j = 0; j < n_out; ++j) {
     if (!is_rout(j) || !res[j] || t->nnz_out[j] == 0) continue;
     const int nnz = static_cast<int>(t->nnz_out[j]);
-    if (hp.red.ensure(static_cast<size_t>(nnz))) return 1;
+    if (hp.red.ensure(static_cast<size_t>(nnz)) || hp.red_pin.ensure(static_cast<size_t>(nnz))) return 1;
     CCU_CUDA(ccu::launch_tree(t->d_part[j].p, nblocks, nnz, hp.red.p, s_cmp));
     g_launches++;
-    CCU_CUDA(cudaMemcpyAsync(res[j], hp.red.p, static_cast<size_t>(nnz) * 8, cudaMemcpyDeviceToHost, s_cmp));
+    CCU_CUDA(cudaMemcpyAsync(hp.red_pin.p, hp.red.p, static_cast<size_t>(nnz) * 8, cudaMemcpyDeviceToHost, s_cmp));
     CCU_CUDA(cudaStreamSynchronize(s_cmp));  // hp.red is reused by the next reduced output
+    std::memcpy(res[j], hp.red_pin.p, static_cast<size_t>(nnz) * 8);
   }
-  cudaError_t e0 = cudaStreamSynchronize(s_h2d), e1 = cudaStreamSynchronize(s_cmp), e2 = cudaStreamSynchronize(s_d2h);
+  harvest(0);
+  harvest(1);
+  return 0;
+}
+
+static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res,
+                          const int* reduce_in, const int* reduce_out) {
+  if (check_eval_args(t, N)) return 1;
+  if (!arg || !res) return fail("null argument / result array");
+  CCU_CUDA(cudaSetDevice(t->device));
+  const size_t n_in = t->nnz_in.size(), n_out = t->nnz_out.size();
+  HostPipe& hp = t->pipe;
+  if (!hp.ready) {
+    for (int k = 0; k < 3; ++k) CCU_CUDA(cudaStreamCreateWithFlags(&hp.s[k], cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      for (int k = 0; k < 3; ++k) CCU_CUDA(cudaEventCreateWithFlags(&hp.ev[b][k], cudaEventDisableTiming));
+      for (int k = 0; k < 6; ++k) CCU_CUDA(cudaEventCreate(&hp.tev[b][k]));
+    }
+    for (int b = 0; b < 2; ++b) {
+      hp.in_aos[b].resize(n_in); hp.in_soa[b].resize(n_in); hp.out_aos[b].resize(n_out); hp.out_soa[b].resize(n_out);
+      hp.in_pin[b].resize(n_in); hp.out_pin[b].resize(n_out);
+    }
+    hp.bcast.resize(n_in);
+    hp.ready = true;
+  }
+  t->st_h2d_ms = t->st_kernel_ms = t->st_d2h_ms = t->st_stage_ms = t->st_wall_ms = t->st_staged_bytes = 0;
+  hp.tev_used[0] = hp.tev_used[1] = false;
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc = eval_host_chunks(t, N, arg, res, reduce_in, reduce_out);
+  const std::string first_error = rc ? g_err : std::string();
+  // Whatever happened, nothing may still read the caller's inputs or write the caller's outputs after the return
+  cudaError_t e0 = cudaStreamSynchronize(hp.s[0]), e1 = cudaStreamSynchronize(hp.s[1]), e2 = cudaStreamSynchronize(hp.s[2]);
   cudaError_t e = e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2);
   if (rc == 0 && e != cudaSuccess) rc = fail("evaluation failed on device: %s", cudaGetErrorString(e));
+  else if (rc) { g_err = first_error; cudaGetLastError(); }
+  t->st_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return rc;
 }
 
@@ -930,6 +1125,13 @@ int ccu_tape_last_kernel_ms(ccu_tape* t, double* ms) {
   float f = 0;
   CCU_CUDA(cudaEventElapsedTime(&f, t->ev0, t->ev1));
   *ms = f;
+  return 0;
+}
+
+int ccu_tape_last_eval_stats(const ccu_tape* t, double stats[6]) {
+  if (!t || !stats) return fail("null argument");
+  stats[0] = t->st_h2d_ms; stats[1] = t->st_kernel_ms; stats[2] = t->st_d2h_ms; stats[3] = t->st_stage_ms;
+  stats[4] = t->st_wall_ms; stats[5] = t->st_staged_bytes;
   return 0;
 }
 

@@ -122,6 +122,12 @@ class CudaTape:
         capi.check(capi.lib().ccu_tape_last_kernel_ms(self.handle, ctypes.byref(ms)))
         return ms.value
 
+    def last_eval_stats(self):
+        """Phase times of the last host-pointer evaluation (ccu_tape_last_eval_stats)."""
+        st = (ctypes.c_double * 6)()
+        capi.check(capi.lib().ccu_tape_last_eval_stats(self.handle, st))
+        return dict(h2d_ms=st[0], kernel_ms=st[1], d2h_ms=st[2], stage_ms=st[3], wall_ms=st[4], staged_bytes=st[5])
+
     # -- device-pointer evaluation (roofline path) --------------------------------------------------
     def eval_device(self, N, d_arg, d_res, layout=LAYOUT_SOA, stream=0, reduce_in=None, reduce_out=None):
         """d_arg/d_res: device addresses (int) or None."""

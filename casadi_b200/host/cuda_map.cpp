@@ -29,6 +29,7 @@ namespace casadi {
       void (*tape_destroy)(void*) = nullptr;
       int (*map_eval_host)(void*, ccu_int, const double* const*, double* const*) = nullptr;
       int (*map_eval_reduce_host)(void*, ccu_int, const double* const*, double* const*, const int*, const int*) = nullptr;
+      int (*last_eval_stats)(const void*, double*) = nullptr;
       // tape builder (MX functions that cannot be expanded are lowered to one scalar tape)
       void* (*builder_create)() = nullptr;
       void (*builder_destroy)(void*) = nullptr;
@@ -66,6 +67,7 @@ namespace casadi {
         lib.map_eval_host = reinterpret_cast<decltype(lib.map_eval_host)>(sym("ccu_map_eval_host"));
         lib.map_eval_reduce_host =
           reinterpret_cast<decltype(lib.map_eval_reduce_host)>(sym("ccu_map_eval_reduce_host"));
+        lib.last_eval_stats = reinterpret_cast<decltype(lib.last_eval_stats)>(sym("ccu_tape_last_eval_stats"));
         lib.builder_create = reinterpret_cast<decltype(lib.builder_create)>(sym("ccu_builder_create"));
         lib.builder_destroy = reinterpret_cast<decltype(lib.builder_destroy)>(sym("ccu_builder_destroy"));
         lib.builder_const = reinterpret_cast<decltype(lib.builder_const)>(sym("ccu_builder_const"));
@@ -470,7 +472,13 @@ namespace casadi {
                               static_cast<ccu_int>(t.nnz_out.size()), get_ptr(t.nnz_out), device_);
     casadi_assert(m->tape!=nullptr, "Map 'cuda': cannot put function '" + f_.name() + "' on device "
                   + str(device_) + ": " + std::string(lib.last_error()));
+    // FStats (timing.hpp:47-98): the whole call, and the device time of its three phases (they overlap chunk by chunk,
+    // so the parts do not add up to the whole) plus the host time spent staging pageable buffers
     m->add_stat("cuda");
+    m->add_stat("cuda_h2d");
+    m->add_stat("cuda_kernel");
+    m->add_stat("cuda_d2h");
+    m->add_stat("cuda_stage");
     return 0;
   }
 
@@ -513,6 +521,17 @@ namespace casadi {
       flag = lib.map_eval_host(m->tape, n_*rep_, arg, res);
     }
     m->fstats.at("cuda").toc();
+    {
+      double st[6] = {0, 0, 0, 0, 0, 0};
+      if (lib.last_eval_stats(m->tape, st) == 0) {
+        const char* names[4] = {"cuda_h2d", "cuda_kernel", "cuda_d2h", "cuda_stage"};
+        for (int k = 0; k < 4; ++k) {
+          FStats& fs = m->fstats.at(names[k]);
+          fs.n_call += 1;
+          fs.t_wall += 1e-3 * st[k];
+        }
+      }
+    }
     if (!flag && n_failed > 0) {
       casadi_warning("Map 'cuda': linear solver factorization failed for " + str(static_cast<casadi_int>(n_failed))
                      + " of " + str(n_) + " instances of '" + f_.name() + "'");

@@ -243,6 +243,13 @@ CCU_EXPORT int ccu_linsol_solve_device(ccu_linsol* ls, ccu_int N, const double* 
 /* Time (ms) of the most recent kernel launch sequence of this tape, measured with CUDA events on
  * the launching stream (synchronises).  FStats analogue (casadi/core/timing.hpp:47-98). */
 CCU_EXPORT int ccu_tape_last_kernel_ms(ccu_tape* t, double* ms);
+/* Phase times of the most recent ccu_map_eval_host / ccu_map_eval_reduce_host call on this tape -- the split the
+ * reference's FStats would record around the three phases (casadi/core/timing.hpp:47-98,
+ * function_internal.cpp:986-1011): stats[0] = H2D, [1] = kernels (layout + tape + reduction), [2] = D2H, each the
+ * device time summed over the chunks (the phases overlap, so they do not add up to the wall time), [3] = time the
+ * calling thread spent copying between pageable caller memory and the pinned staging, [4] = wall time of the call,
+ * all in ms; [5] = bytes that went through the pinned staging (0 when every caller buffer was page-locked). */
+CCU_EXPORT int ccu_tape_last_eval_stats(const ccu_tape* t, double stats[6]);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 CCU_EXPORT ccu_int ccu_launch_count(void);
 /* Measured FP64 non-FMA issue rate (DADD/s) of `device`: the FP64 denominator of the roofline (SURVEY 8d;

@@ -428,3 +428,26 @@ def test_full_size_interpreter_matches_specialised_kernels_on_every_tile():
     for j, (x, y) in enumerate(zip(a, b)):
         assert bool((x.view(torch.int64) == y.view(torch.int64)).all()), "quad out%d interp vs jit at N=1e6" % j
     _assert_every_period_equals_the_first(a, P, N, "quad (interp)")
+
+
+def test_host_path_pageable_staging_and_phase_stats(monkeypatch):
+    """ccu_map_eval_host on ordinary (pageable) numpy buffers goes through the library's pinned staging; with
+    CCU_HOST_STAGING=0 the driver stages the copies itself.  Same bits either way, ragged chunks included, and the
+    phase statistics (FStats split h2d / kernel / d2h) are filled in."""
+    tape, case = load_tape("quad"), load_case("quad")
+    P, reps = case["N"], 1500
+    N = P * reps - 13
+    ins = [np.tile(a, reps)[:N * int(n)] for a, n in zip(case["in"], tape["nnz_in"])]
+    t = CudaTape(tape, mode="jit")
+    monkeypatch.setenv("CCU_HOST_CHUNK", "16384")
+    staged = CudaMap(t, N)(ins)
+    st = t.last_eval_stats()
+    assert st["staged_bytes"] == 8 * N * (sum(t.nnz_in) + sum(t.nnz_out))
+    assert st["h2d_ms"] > 0 and st["kernel_ms"] > 0 and st["d2h_ms"] > 0 and st["wall_ms"] > 0 and st["stage_ms"] > 0
+    monkeypatch.setenv("CCU_HOST_STAGING", "0")
+    direct = CudaMap(t, N)(ins)
+    assert t.last_eval_stats()["staged_bytes"] == 0
+    for j, (a, b) in enumerate(zip(staged, direct)):
+        assert_bit_equal(a, b, "pinned staging vs driver-staged copies, out%d" % j)
+    got = staged[0].reshape(N, -1)
+    assert_bit_equal(got[P * (reps - 2):P * (reps - 1)].ravel(), got[:P].ravel(), "a late period vs period 0")
