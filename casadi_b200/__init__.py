@@ -7,6 +7,6 @@ Package layout
   cuda_map.py  Python mirror of the Map interface (used by tests and bench.py)
 """
 from .capi import CcuError, LAYOUT_AOS, LAYOUT_SOA  # noqa: F401
-from .cuda_map import CudaMap, CudaTape  # noqa: F401
+from .cuda_map import CudaMap, CudaMultiMap, CudaTape  # noqa: F401
 from .linsol import CudaLinsol  # noqa: F401
 from .tapeio import load_case, load_tape  # noqa: F401

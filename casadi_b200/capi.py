@@ -49,6 +49,20 @@ SYMBOLS = {
     "ccu_map_eval_reduce_device": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_i_p, c_i_p, ctypes.c_int, c_vp]),
     "ccu_map_eval_shard_device": (ctypes.c_int, [c_vp, c_ll, c_ll, c_ll, c_vp, c_vp, c_i_p, c_i_p, c_vp, ctypes.c_int, c_vp]),
     "ccu_reduce_tree_device": (ctypes.c_int, [ctypes.c_int, c_vp, c_ll, c_ll, c_vp, c_vp]),
+    "ccu_comm_available": (ctypes.c_int, []),
+    "ccu_comm_nccl_version": (ctypes.c_int, []),
+    "ccu_comm_create_all": (c_vp, [ctypes.c_int, c_i_p]),
+    "ccu_comm_unique_id": (ctypes.c_int, [c_vp]),
+    "ccu_comm_create_rank": (c_vp, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "ccu_comm_destroy": (None, [c_vp]),
+    "ccu_comm_size": (ctypes.c_int, [c_vp]),
+    "ccu_comm_allreduce_block_sums": (ctypes.c_int, [c_vp, c_vp, c_ll, c_vp]),
+    "ccu_multi_create": (c_vp, [c_ll, c_i_p, c_i_p, c_i_p, c_i_p, c_d_p, c_ll, c_ll, c_ll_p, c_ll, c_ll_p, ctypes.c_int, c_i_p]),
+    "ccu_builder_finish_multi": (c_vp, [c_vp, c_ll, c_ll_p, c_ll, c_ll_p, ctypes.c_int, c_i_p]),
+    "ccu_multi_destroy": (None, [c_vp]),
+    "ccu_multi_size": (ctypes.c_int, [c_vp]),
+    "ccu_multi_tape": (c_vp, [c_vp, ctypes.c_int]),
+    "ccu_multi_eval_host": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_i_p, c_i_p]),
     "ccu_builder_create": (c_vp, []),
     "ccu_builder_destroy": (None, [c_vp]),
     "ccu_builder_const": (c_ll, [c_vp, ctypes.c_double]),

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "ccu_isa.h"
+#include "comm.hpp"
 #include "interp.cuh"
 #include "jit.hpp"
 #include "layout.cuh"
@@ -742,8 +743,12 @@ int ccu_reduce_tree_device(int device, double* d_part, ccu_int N_global, ccu_int
 // the device works on the neighbouring chunks; page-locked buffers are used directly.  Chunks are multiples of
 // kReduceBlock, so reduce_out block sums land at their global positions and the summation tree is the same as for a
 // single launch.
+// (g_off, N_glob): position of these N instances inside the whole batch when the batch is sharded over several devices
+// (ccu_multi); the block sums of reduced outputs are then written at their GLOBAL rows of d_part and the cross-device
+// combine + level-1 tree is left to the caller (finish_reduce == false).
 static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res,
-                            const int* reduce_in, const int* reduce_out) {
+                            const int* reduce_in, const int* reduce_out, long long g_off, long long N_glob,
+                            bool finish_reduce) {
   const size_t n_in = t->nnz_in.size(), n_out = t->nnz_out.size();
   HostPipe& hp = t->pipe;
   cudaStream_t s_h2d = hp.s[0], s_cmp = hp.s[1], s_d2h = hp.s[2];
@@ -753,7 +758,8 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
   else C = std::max<long long>(1 << 16, std::min<long long>(1 << 20, C));
   C = std::max<long long>(ccu::kReduceBlock, (C + ccu::kReduceBlock - 1) / ccu::kReduceBlock * ccu::kReduceBlock);
   const long long nchunks = N > 0 ? (N + C - 1) / C : 0;
-  const long long nblocks = (N + ccu::kReduceBlock - 1) / ccu::kReduceBlock;
+  const long long nblocks = (N_glob + ccu::kReduceBlock - 1) / ccu::kReduceBlock;
+  const long long blk_off = g_off / ccu::kReduceBlock;
   auto is_rin = [&](size_t j) { return reduce_in && reduce_in[j]; };
   auto is_rout = [&](size_t j) { return reduce_out && reduce_out[j]; };
   // which caller buffers need pinned staging
@@ -776,6 +782,9 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
   for (size_t j = 0; j < n_out; ++j) {
     if (!is_rout(j) || !res[j] || t->nnz_out[j] == 0) continue;
     if (t->d_part[j].ensure(static_cast<size_t>(std::max<long long>(nblocks, 1)) * t->nnz_out[j])) return 1;
+    // a shard owns only its rows: the others must read as zero for the cross-device combine
+    if (!finish_reduce)
+      CCU_CUDA(cudaMemsetAsync(t->d_part[j].p, 0, static_cast<size_t>(std::max<long long>(nblocks, 1)) * t->nnz_out[j] * 8, s_cmp));
   }
   // accumulate the phase times of the chunk that used slot b last
   auto harvest = [&](int b) {
@@ -867,7 +876,7 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
       if (!d_res[j]) continue;
       const int nnz = static_cast<int>(t->nnz_out[j]);
       if (is_rout(j)) {
-        CCU_CUDA(ccu::launch_block_sums(d_res[j], 1, n, n, nnz, t->d_part[j].p + (i0 / ccu::kReduceBlock) * nnz, s_cmp));
+        CCU_CUDA(ccu::launch_block_sums(d_res[j], 1, n, n, nnz, t->d_part[j].p + (blk_off + i0 / ccu::kReduceBlock) * nnz, s_cmp));
       } else {
         CCU_CUDA(ccu::launch_soa_to_aos(d_res[j], hp.out_aos[b][j].p, n, nnz, n, s_cmp));
       }
@@ -891,7 +900,7 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
   }
   if (nchunks > 0 && copy_out(nchunks - 1)) return 1;
   // reduced outputs: level-1 tree over the block sums, then a tiny D2H
-  for (size_t j = 0; j < n_out; ++j) {
+  for (size_t j = 0; j < n_out && finish_reduce; ++j) {
     if (!is_rout(j) || !res[j] || t->nnz_out[j] == 0) continue;
     const int nnz = static_cast<int>(t->nnz_out[j]);
     if (hp.red.ensure(static_cast<size_t>(nnz)) || hp.red_pin.ensure(static_cast<size_t>(nnz))) return 1;
@@ -907,7 +916,9 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
 }
 
 static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res,
-                          const int* reduce_in, const int* reduce_out) {
+                          const int* reduce_in, const int* reduce_out, long long g_off = 0, long long N_glob = -1,
+                          bool finish_reduce = true) {
+  if (N_glob < 0) N_glob = N;
   if (check_eval_args(t, N)) return 1;
   if (!arg || !res) return fail("null argument / result array");
   CCU_CUDA(cudaSetDevice(t->device));
@@ -929,7 +940,7 @@ static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, doub
   t->st_h2d_ms = t->st_kernel_ms = t->st_d2h_ms = t->st_stage_ms = t->st_wall_ms = t->st_staged_bytes = 0;
   hp.tev_used[0] = hp.tev_used[1] = false;
   const auto t0 = std::chrono::steady_clock::now();
-  int rc = eval_host_chunks(t, N, arg, res, reduce_in, reduce_out);
+  int rc = eval_host_chunks(t, N, arg, res, reduce_in, reduce_out, g_off, N_glob, finish_reduce);
   const std::string first_error = rc ? g_err : std::string();
   // Whatever happened, nothing may still read the caller's inputs or write the caller's outputs after the return
   cudaError_t e0 = cudaStreamSynchronize(hp.s[0]), e1 = cudaStreamSynchronize(hp.s[1]), e2 = cudaStreamSynchronize(hp.s[2]);
@@ -947,6 +958,188 @@ int ccu_map_eval_host(ccu_tape* t, ccu_int N, const double* const* arg, double* 
 int ccu_map_eval_reduce_host(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res,
                              const int* reduce_in, const int* reduce_out) {
   return eval_host_impl(t, N, arg, res, reduce_in, reduce_out);
+}
+
+// ------------------------------------------------------------------------------- communicators (comm.cu)
+struct ccu_comm {
+  ccu::Comm* c = nullptr;
+};
+
+int ccu_comm_available(void) {
+  std::string why;
+  if (ccu::comm_available(&why)) return 1;
+  fail("%s", why.c_str());
+  return 0;
+}
+
+int ccu_comm_unique_id(unsigned char id[128]) {
+  std::string err;
+  if (!id) return fail("null id");
+  if (!ccu::comm_unique_id(id, &err)) return fail("%s", err.c_str());
+  return 0;
+}
+
+ccu_comm* ccu_comm_create_all(int n_devices, const int* devices) {
+  if (n_devices < 1) { fail("ccu_comm_create_all: no devices"); return nullptr; }
+  std::vector<int> dv(n_devices);
+  for (int k = 0; k < n_devices; ++k) dv[k] = devices ? devices[k] : k;
+  std::string err;
+  ccu::Comm* c = ccu::comm_create_all(dv, &err);
+  if (!c) { fail("%s", err.c_str()); return nullptr; }
+  ccu_comm* h = new ccu_comm();
+  h->c = c;
+  return h;
+}
+
+ccu_comm* ccu_comm_create_rank(const unsigned char id[128], int rank, int n_ranks, int device) {
+  if (!id || rank < 0 || rank >= n_ranks) { fail("ccu_comm_create_rank: invalid arguments"); return nullptr; }
+  std::string err;
+  ccu::Comm* c = ccu::comm_create_rank(id, rank, n_ranks, device, &err);
+  if (!c) { fail("%s", err.c_str()); return nullptr; }
+  ccu_comm* h = new ccu_comm();
+  h->c = c;
+  return h;
+}
+
+void ccu_comm_destroy(ccu_comm* h) {
+  if (!h) return;
+  ccu::comm_destroy(h->c);
+  delete h;
+}
+
+int ccu_comm_size(const ccu_comm* h) { return h ? ccu::comm_size(h->c) : 0; }
+int ccu_comm_nccl_version(void) { return ccu::comm_nccl_version(); }
+
+int ccu_comm_allreduce_block_sums(ccu_comm* h, double* const* d_part, ccu_int count, void* const* streams) {
+  if (!h || !d_part) return fail("ccu_comm_allreduce_block_sums: null argument");
+  const int nl = ccu::comm_local_size(h->c);
+  std::vector<cudaStream_t> st(nl, nullptr);
+  for (int k = 0; k < nl; ++k) st[k] = streams ? static_cast<cudaStream_t>(streams[k]) : nullptr;
+  std::string err;
+  if (!ccu::comm_allreduce_bits(h->c, d_part, count, st.data(), &err)) return fail("%s", err.c_str());
+  g_launches += nl;
+  return 0;
+}
+
+// ---------------------------------------------------------------- one tape replicated on several devices
+struct ccu_multi {
+  std::vector<ccu_tape*> tapes;  // one replica per device
+  ccu_comm* comm = nullptr;      // null for a single device
+};
+
+static ccu_multi* multi_finish(std::vector<ccu_tape*>& tapes, int n_devices, const int* devices) {
+  ccu_multi* m = new ccu_multi();
+  m->tapes = tapes;
+  if (n_devices > 1) {
+    m->comm = ccu_comm_create_all(n_devices, devices);
+    if (!m->comm) {
+      const std::string e = g_err;
+      for (ccu_tape* t : tapes) ccu_tape_destroy(t);
+      delete m;
+      g_err = "multi-device map needs NCCL: " + e;
+      return nullptr;
+    }
+  }
+  return m;
+}
+
+ccu_multi* ccu_multi_create(ccu_int n_instr, const int* op, const int* i0, const int* i1, const int* i2, const double* d,
+                            ccu_int sz_w, ccu_int n_in, const ccu_int* nnz_in, ccu_int n_out, const ccu_int* nnz_out,
+                            int n_devices, const int* devices) {
+  if (n_devices < 1 || !devices) { fail("ccu_multi_create: no devices"); return nullptr; }
+  std::vector<ccu_tape*> tapes;
+  for (int k = 0; k < n_devices; ++k) {
+    // (the specialised kernels of the replicas come out of the on-disk cubin cache after the first device)
+    ccu_tape* t = ccu_tape_create(n_instr, op, i0, i1, i2, d, sz_w, n_in, nnz_in, n_out, nnz_out, devices[k]);
+    if (!t) { for (ccu_tape* u : tapes) ccu_tape_destroy(u); return nullptr; }
+    tapes.push_back(t);
+  }
+  return multi_finish(tapes, n_devices, devices);
+}
+
+ccu_multi* ccu_builder_finish_multi(ccu_builder* b, ccu_int n_in, const ccu_int* nnz_in, ccu_int n_out, const ccu_int* nnz_out,
+                                    int n_devices, const int* devices) {
+  if (n_devices < 1 || !devices) { fail("ccu_builder_finish_multi: no devices"); return nullptr; }
+  std::vector<ccu_tape*> tapes;
+  for (int k = 0; k < n_devices; ++k) {
+    ccu_tape* t = ccu_builder_finish(b, n_in, nnz_in, n_out, nnz_out, devices[k]);
+    if (!t) { for (ccu_tape* u : tapes) ccu_tape_destroy(u); return nullptr; }
+    tapes.push_back(t);
+  }
+  return multi_finish(tapes, n_devices, devices);
+}
+
+void ccu_multi_destroy(ccu_multi* m) {
+  if (!m) return;
+  for (ccu_tape* t : m->tapes) ccu_tape_destroy(t);
+  ccu_comm_destroy(m->comm);
+  delete m;
+}
+
+int ccu_multi_size(const ccu_multi* m) { return m ? static_cast<int>(m->tapes.size()) : 0; }
+ccu_tape* ccu_multi_tape(ccu_multi* m, int k) {
+  return (m && k >= 0 && k < static_cast<int>(m->tapes.size())) ? m->tapes[k] : nullptr;
+}
+
+// Instances [g*N/G, (g+1)*N/G) in whole reduction blocks on device g, each shard through the chunked host pipeline of its
+// own device from its own host thread; reduced outputs: block sums at global rows, one NCCL all-reduce over the devices,
+// level-1 tree on device 0 (HorzRepsum / MapSum semantics, repmat.cpp:127-135, mapsum.cpp:170-184).
+int ccu_multi_eval_host(ccu_multi* m, ccu_int N, const double* const* arg, double* const* res, const int* reduce_in,
+                        const int* reduce_out) {
+  if (!m || m->tapes.empty()) return fail("null multi-device map");
+  const int G = static_cast<int>(m->tapes.size());
+  if (G == 1) return eval_host_impl(m->tapes[0], N, arg, res, reduce_in, reduce_out);
+  if (check_eval_args(m->tapes[0], N)) return 1;
+  ccu_tape* t0 = m->tapes[0];
+  const size_t n_in = t0->nnz_in.size(), n_out = t0->nnz_out.size();
+  const long long blocks = (N + ccu::kReduceBlock - 1) / ccu::kReduceBlock;
+  std::vector<long long> off(G + 1, 0);
+  for (int g = 0; g <= G; ++g) {
+    const long long per = blocks / G, extra = blocks % G;
+    const long long b0 = g * per + std::min<long long>(g, extra);
+    off[g] = std::min<long long>(b0 * ccu::kReduceBlock, N);
+  }
+  bool any_red = false;
+  for (size_t j = 0; j < n_out; ++j) any_red = any_red || (reduce_out && reduce_out[j] && res[j] && t0->nnz_out[j] > 0);
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> errs(G);
+  std::vector<std::thread> th;
+  for (int g = 0; g < G; ++g) {
+    th.emplace_back([&, g] {
+      const long long i0 = off[g], n = off[g + 1] - off[g];
+      std::vector<const double*> a(n_in, nullptr);
+      std::vector<double*> r(n_out, nullptr);
+      for (size_t j = 0; j < n_in; ++j)
+        a[j] = arg[j] ? ((reduce_in && reduce_in[j]) ? arg[j] : arg[j] + i0 * t0->nnz_in[j]) : nullptr;
+      for (size_t j = 0; j < n_out; ++j)
+        r[j] = res[j] ? ((reduce_out && reduce_out[j]) ? res[j] : res[j] + i0 * t0->nnz_out[j]) : nullptr;
+      rcs[g] = eval_host_impl(m->tapes[g], n, a.data(), r.data(), reduce_in, reduce_out, i0, N, /*finish_reduce=*/false);
+      if (rcs[g]) errs[g] = g_err;
+    });
+  }
+  for (auto& x : th) x.join();
+  for (int g = 0; g < G; ++g) if (rcs[g]) return fail("device %d: %s", m->tapes[g]->device, errs[g].c_str());
+  if (!any_red) return 0;
+  for (size_t j = 0; j < n_out; ++j) {
+    if (!(reduce_out && reduce_out[j] && res[j] && t0->nnz_out[j] > 0)) continue;
+    const int nnz = static_cast<int>(t0->nnz_out[j]);
+    std::vector<double*> bufs(G);
+    std::vector<void*> streams(G);
+    for (int g = 0; g < G; ++g) { bufs[g] = m->tapes[g]->d_part[j].p; streams[g] = m->tapes[g]->pipe.s[1]; }
+    if (ccu_comm_allreduce_block_sums(m->comm, bufs.data(), std::max<long long>(blocks, 1) * nnz, streams.data())) return 1;
+    CCU_CUDA(cudaSetDevice(t0->device));
+    HostPipe& hp = t0->pipe;
+    if (hp.red.ensure(static_cast<size_t>(nnz)) || hp.red_pin.ensure(static_cast<size_t>(nnz))) return 1;
+    CCU_CUDA(ccu::launch_tree(t0->d_part[j].p, blocks, nnz, hp.red.p, hp.s[1]));
+    g_launches++;
+    CCU_CUDA(cudaMemcpyAsync(hp.red_pin.p, hp.red.p, static_cast<size_t>(nnz) * 8, cudaMemcpyDeviceToHost, hp.s[1]));
+    for (int g = 0; g < G; ++g) {
+      CCU_CUDA(cudaSetDevice(m->tapes[g]->device));
+      CCU_CUDA(cudaStreamSynchronize(m->tapes[g]->pipe.s[1]));
+    }
+    std::memcpy(res[j], hp.red_pin.p, static_cast<size_t>(nnz) * 8);
+  }
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------- tape builder

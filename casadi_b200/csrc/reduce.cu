@@ -11,8 +11,8 @@
 //   level 1: the block sums are combined by the same balanced pairwise tree over the block index,
 //            padded with +0.0 to the next power of two.
 // Multi-GPU: shards are whole blocks, every rank contributes its block sums at their global
-// positions (zeros elsewhere, so an NCCL sum is exact) and level 1 is evaluated on the gathered
-// vector -- see comm.cu.
+// positions (zeros elsewhere, so an NCCL sum of the bit patterns is exact) and level 1 is evaluated on
+// the merged vector -- see comm.cu and ccu_multi_eval_host (capi.cu).
 #include "reduce.cuh"
 
 namespace ccu {

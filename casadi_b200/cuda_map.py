@@ -191,3 +191,52 @@ class CudaMap:
                 f.handle, N, a, r, None if ri is None else ri.ctypes.data_as(capi.c_i_p),
                 None if ro is None else ro.ctypes.data_as(capi.c_i_p)))
         return outs
+
+
+class CudaMultiMap:
+    """f.map(N, "cuda") sharded over several devices of THIS process (ccu_multi): what the C++ CudaMap builds for
+    CASADI_CUDA_DEVICES.  Device g evaluates instances [g*N/G, (g+1)*N/G); reduce_out sums are merged by NCCL
+    inside the library.  Host buffers in the reference's AoS layout, as for CudaMap."""
+
+    def __init__(self, tape, n, devices, reduce_in=None, reduce_out=None, mode=None):
+        L = capi.lib()
+        self.nnz_in = [int(v) for v in tape["nnz_in"]]
+        self.nnz_out = [int(v) for v in tape["nnz_out"]]
+        self.n = int(n)
+        self.reduce_in = list(reduce_in) if reduce_in is not None else None
+        self.reduce_out = list(reduce_out) if reduce_out is not None else None
+        arrs = [np.ascontiguousarray(tape[k], np.int32) for k in ("op", "i0", "i1", "i2")]
+        d = np.ascontiguousarray(tape["d"], np.float64)
+        nin, nout = np.ascontiguousarray(self.nnz_in, np.int64), np.ascontiguousarray(self.nnz_out, np.int64)
+        dv = np.ascontiguousarray(list(devices), np.int32)
+        capi.check(L.ccu_set_default_mode(capi.MODES[mode]))
+        try:
+            self.handle = L.ccu_multi_create(len(d), *[a.ctypes.data_as(capi.c_i_p) for a in arrs], d.ctypes.data_as(capi.c_d_p),
+                                             int(tape["sz_w"]), len(nin), nin.ctypes.data_as(capi.c_ll_p), len(nout),
+                                             nout.ctypes.data_as(capi.c_ll_p), len(dv), dv.ctypes.data_as(capi.c_i_p))
+        finally:
+            L.ccu_set_default_mode(-1)
+        if not self.handle:
+            raise CcuError(capi.last_error())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            capi.lib().ccu_multi_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __call__(self, args):
+        N = self.n
+        ins = [None if a is None else np.ascontiguousarray(a, np.float64).ravel() for a in args]
+        outs = [np.full(nz * (1 if (self.reduce_out and self.reduce_out[j]) else N), np.nan) for j, nz in enumerate(self.nnz_out)]
+        a = capi.ptr_array([None if x is None or x.size == 0 else x.ctypes.data for x in ins])
+        r = capi.ptr_array([None if x.size == 0 else x.ctypes.data for x in outs])
+        ri, ro = capi.int_array(self.reduce_in), capi.int_array(self.reduce_out)
+        capi.check(capi.lib().ccu_multi_eval_host(self.handle, N, a, r, None if ri is None else ri.ctypes.data_as(capi.c_i_p),
+                                                  None if ro is None else ro.ctypes.data_as(capi.c_i_p)))
+        return outs

@@ -1,10 +1,16 @@
 """Multi-GPU evaluation of a mapped tape: one process per GPU (torch.distributed), contiguous shards of whole
 1024-instance reduction blocks, tape replicated, NO data-path collective for plain maps.  Only reduce_out
 communicates: every rank writes the level-0 sums of its blocks at their global positions into a zero vector, one
-all-reduce (NCCL over NVLink on GPUs; gloo in the CPU tests) sums the disjoint supports exactly, and every rank
-evaluates the same level-1 tree -- the result is bit-identical for 1/2/4/8 GPUs (HorzRepsum/MapSum semantics up to
-the documented summation order, casadi/core/repmat.cpp:127-135, mapsum.cpp:154-186).
+all-reduce merges the disjoint supports exactly, and every rank evaluates the same level-1 tree -- the result is
+bit-identical for 1/2/4/8 GPUs (HorzRepsum/MapSum semantics up to the documented summation order,
+casadi/core/repmat.cpp:127-135, mapsum.cpp:154-186).
+
+On GPUs the all-reduce is issued by libcasadi_cuda.so itself (ccu_comm_allreduce_block_sums: NCCL over NVLink on the
+64-bit patterns, csrc/comm.cu); torch.distributed only carries the 128-byte NCCL id from rank 0 to the others when
+the communicator is created.  The gloo path (CPU tests of the host logic) sums the float64 vectors.
 """
+import ctypes
+
 import numpy as np
 
 from . import capi
@@ -63,6 +69,31 @@ class ShardedCudaMap:
         nb = (self.N + BLOCK - 1) // BLOCK
         self.part = [torch.zeros((nb, nnz), dtype=torch.float64, device=self.dev)
                      if (self.reduce_out and self.reduce_out[j]) else None for j, nnz in enumerate(tape.nnz_out)]
+        # the library's own NCCL communicator for this rank (ncclCommInitRank; id broadcast from rank 0)
+        self.comm = None
+        if self.world > 1 and any(p is not None for p in self.part):
+            L = capi.lib()
+            idbuf = (ctypes.c_ubyte * 128)()
+            if self.rank == 0:
+                capi.check(L.ccu_comm_unique_id(idbuf))
+            backend = dist.get_backend(group)
+            idt = torch.tensor(list(idbuf), dtype=torch.uint8, device=self.dev if backend == "nccl" else "cpu")
+            dist.broadcast(idt, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            idbuf = (ctypes.c_ubyte * 128)(*idt.cpu().tolist())
+            self.comm = L.ccu_comm_create_rank(idbuf, self.rank, self.world, tape.device)
+            if not self.comm:
+                raise capi.CcuError(capi.last_error())
+
+    def close(self):
+        if getattr(self, "comm", None):
+            capi.lib().ccu_comm_destroy(self.comm)
+            self.comm = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def eval_device(self, d_arg, d_res, layout=LAYOUT_SOA, stream=None):
         """d_arg[j]: device address of this SHARD's input j (or of the single instance for reduce_in inputs);
@@ -71,9 +102,10 @@ class ShardedCudaMap:
         import torch
         L = capi.lib()
         s = stream if stream is not None else torch.cuda.current_stream(self.dev)
-        for p in self.part:
-            if p is not None:
-                p.zero_()
+        with torch.cuda.stream(s):  # the zeroing is ordered with the block sums and the tree of the previous call
+            for p in self.part:
+                if p is not None:
+                    p.zero_()
         ri, ro = capi.int_array(self.reduce_in), capi.int_array(self.reduce_out)
         parts = capi.ptr_array([None if p is None else p.data_ptr() for p in self.part])
         capi.check(L.ccu_map_eval_shard_device(
@@ -83,6 +115,10 @@ class ShardedCudaMap:
         for j, p in enumerate(self.part):
             if p is None:
                 continue
-            with torch.cuda.stream(s):
-                combine_block_sums(p, self.group)
+            if self.comm:
+                capi.check(L.ccu_comm_allreduce_block_sums(self.comm, capi.ptr_array([p.data_ptr()]), p.numel(),
+                                                           capi.ptr_array([s.cuda_stream])))
+            else:
+                with torch.cuda.stream(s):
+                    combine_block_sums(p, self.group)
             capi.check(L.ccu_reduce_tree_device(self.f.device, p.data_ptr(), self.N, self.f.nnz_out[j], d_res[j], s.cuda_stream))

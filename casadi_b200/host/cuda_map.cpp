@@ -9,6 +9,7 @@
 
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -24,11 +25,15 @@ namespace casadi {
       std::string error;
       int (*abi_version)() = nullptr;
       const char* (*last_error)() = nullptr;
-      void* (*tape_create)(ccu_int, const int*, const int*, const int*, const int*, const double*, ccu_int,
-                           ccu_int, const ccu_int*, ccu_int, const ccu_int*, int) = nullptr;
-      void (*tape_destroy)(void*) = nullptr;
-      int (*map_eval_host)(void*, ccu_int, const double* const*, double* const*) = nullptr;
-      int (*map_eval_reduce_host)(void*, ccu_int, const double* const*, double* const*, const int*, const int*) = nullptr;
+      int (*device_count)() = nullptr;
+      // one tape replicated on the devices of this process (a single device is the common case)
+      void* (*multi_create)(ccu_int, const int*, const int*, const int*, const int*, const double*, ccu_int,
+                            ccu_int, const ccu_int*, ccu_int, const ccu_int*, int, const int*) = nullptr;
+      void* (*builder_finish_multi)(void*, ccu_int, const ccu_int*, ccu_int, const ccu_int*, int, const int*) = nullptr;
+      void (*multi_destroy)(void*) = nullptr;
+      int (*multi_size)(const void*) = nullptr;
+      void* (*multi_tape)(void*, int) = nullptr;
+      int (*multi_eval_host)(void*, ccu_int, const double* const*, double* const*, const int*, const int*) = nullptr;
       int (*last_eval_stats)(const void*, double*) = nullptr;
       // tape builder (MX functions that cannot be expanded are lowered to one scalar tape)
       void* (*builder_create)() = nullptr;
@@ -43,7 +48,6 @@ namespace casadi {
                         const ccu_int*, ccu_int*, ccu_int, int, double, ccu_int*) = nullptr;
       int (*builder_mtimes)(void*, const ccu_int*, const ccu_int*, const ccu_int*, const ccu_int*, ccu_int*,
                             const ccu_int*) = nullptr;
-      void* (*builder_finish)(void*, ccu_int, const ccu_int*, ccu_int, const ccu_int*, int) = nullptr;
     };
 
     CudaLib& cuda_lib() {
@@ -62,11 +66,14 @@ namespace casadi {
         auto sym = [&](const char* s) { void* p = dlsym(lib.handle, s); if (!p) ok = false; return p; };
         lib.abi_version = reinterpret_cast<decltype(lib.abi_version)>(sym("ccu_abi_version"));
         lib.last_error = reinterpret_cast<decltype(lib.last_error)>(sym("ccu_last_error"));
-        lib.tape_create = reinterpret_cast<decltype(lib.tape_create)>(sym("ccu_tape_create"));
-        lib.tape_destroy = reinterpret_cast<decltype(lib.tape_destroy)>(sym("ccu_tape_destroy"));
-        lib.map_eval_host = reinterpret_cast<decltype(lib.map_eval_host)>(sym("ccu_map_eval_host"));
-        lib.map_eval_reduce_host =
-          reinterpret_cast<decltype(lib.map_eval_reduce_host)>(sym("ccu_map_eval_reduce_host"));
+        lib.device_count = reinterpret_cast<decltype(lib.device_count)>(sym("ccu_device_count"));
+        lib.multi_create = reinterpret_cast<decltype(lib.multi_create)>(sym("ccu_multi_create"));
+        lib.builder_finish_multi =
+          reinterpret_cast<decltype(lib.builder_finish_multi)>(sym("ccu_builder_finish_multi"));
+        lib.multi_destroy = reinterpret_cast<decltype(lib.multi_destroy)>(sym("ccu_multi_destroy"));
+        lib.multi_size = reinterpret_cast<decltype(lib.multi_size)>(sym("ccu_multi_size"));
+        lib.multi_tape = reinterpret_cast<decltype(lib.multi_tape)>(sym("ccu_multi_tape"));
+        lib.multi_eval_host = reinterpret_cast<decltype(lib.multi_eval_host)>(sym("ccu_multi_eval_host"));
         lib.last_eval_stats = reinterpret_cast<decltype(lib.last_eval_stats)>(sym("ccu_tape_last_eval_stats"));
         lib.builder_create = reinterpret_cast<decltype(lib.builder_create)>(sym("ccu_builder_create"));
         lib.builder_destroy = reinterpret_cast<decltype(lib.builder_destroy)>(sym("ccu_builder_destroy"));
@@ -77,12 +84,11 @@ namespace casadi {
         lib.builder_ldl = reinterpret_cast<decltype(lib.builder_ldl)>(sym("ccu_builder_ldl"));
         lib.builder_qr = reinterpret_cast<decltype(lib.builder_qr)>(sym("ccu_builder_qr"));
         lib.builder_mtimes = reinterpret_cast<decltype(lib.builder_mtimes)>(sym("ccu_builder_mtimes"));
-        lib.builder_finish = reinterpret_cast<decltype(lib.builder_finish)>(sym("ccu_builder_finish"));
         if (!ok) {
           lib.error = "'" + name + "' does not export the casadi_cuda.h entry points";
           lib.handle = nullptr;
-        } else if (lib.abi_version() != 2) {
-          lib.error = "'" + name + "' has ABI version " + str(lib.abi_version()) + ", expected 2";
+        } else if (lib.abi_version() != 3) {
+          lib.error = "'" + name + "' has ABI version " + str(lib.abi_version()) + ", expected 3";
           lib.handle = nullptr;
         }
       });
@@ -442,8 +448,29 @@ namespace casadi {
   }
 
   void CudaMap::init(const Dict& opts) {
-    // Map::create passes an empty Dict (map.cpp:43-47): the device comes from the environment
+    // Map::create passes an empty Dict (map.cpp:43-47): the devices come from the environment.
+    //   CASADI_CUDA_DEVICE=k          one device (default 0)
+    //   CASADI_CUDA_DEVICES=all|0,1,3 several devices of this process: instances [g*n/G, (g+1)*n/G) on device g,
+    //                                 reduce_out sums combined by NCCL inside libcasadi_cuda.so
     if (const char* d = getenv("CASADI_CUDA_DEVICE")) device_ = atoi(d);
+    devices_.clear();
+    if (const char* d = getenv("CASADI_CUDA_DEVICES")) {
+      std::string v = d;
+      if (v == "all") {
+        CudaLib& l = cuda_lib();
+        casadi_assert(l.handle!=nullptr, "Map 'cuda': " + l.error);
+        for (int k = 0; k < l.device_count(); ++k) devices_.push_back(k);
+      } else {
+        size_t pos = 0;
+        while (pos <= v.size()) {
+          size_t c = v.find(',', pos);
+          if (c == std::string::npos) c = v.size();
+          if (c > pos) devices_.push_back(atoi(v.substr(pos, c - pos).c_str()));
+          pos = c + 1;
+        }
+      }
+    }
+    if (devices_.empty()) devices_.push_back(device_);
 
     // Call the initialization method of the base class (work vectors for one serial evaluation are
     // more than the device path needs: no per-instance host work vector is allocated)
@@ -462,16 +489,20 @@ namespace casadi {
     CudaLib& lib = cuda_lib();
     casadi_assert(lib.handle!=nullptr, "Map 'cuda': " + lib.error);
     const Tape& t = tape_;
+    std::vector<int> dv = devices_.empty() ? std::vector<int>{device_} : devices_;
     if (builder_) {
-      m->tape = lib.builder_finish(builder_, static_cast<ccu_int>(t.nnz_in.size()), get_ptr(t.nnz_in),
-                                   static_cast<ccu_int>(t.nnz_out.size()), get_ptr(t.nnz_out), device_);
-    } else
-    m->tape = lib.tape_create(static_cast<ccu_int>(t.op.size()), get_ptr(t.op), get_ptr(t.i0),
-                              get_ptr(t.i1), get_ptr(t.i2), get_ptr(t.d), t.sz_w,
-                              static_cast<ccu_int>(t.nnz_in.size()), get_ptr(t.nnz_in),
-                              static_cast<ccu_int>(t.nnz_out.size()), get_ptr(t.nnz_out), device_);
-    casadi_assert(m->tape!=nullptr, "Map 'cuda': cannot put function '" + f_.name() + "' on device "
-                  + str(device_) + ": " + std::string(lib.last_error()));
+      m->tape = lib.builder_finish_multi(builder_, static_cast<ccu_int>(t.nnz_in.size()), get_ptr(t.nnz_in),
+                                         static_cast<ccu_int>(t.nnz_out.size()), get_ptr(t.nnz_out),
+                                         static_cast<int>(dv.size()), get_ptr(dv));
+    } else {
+      m->tape = lib.multi_create(static_cast<ccu_int>(t.op.size()), get_ptr(t.op), get_ptr(t.i0),
+                                 get_ptr(t.i1), get_ptr(t.i2), get_ptr(t.d), t.sz_w,
+                                 static_cast<ccu_int>(t.nnz_in.size()), get_ptr(t.nnz_in),
+                                 static_cast<ccu_int>(t.nnz_out.size()), get_ptr(t.nnz_out),
+                                 static_cast<int>(dv.size()), get_ptr(dv));
+    }
+    casadi_assert(m->tape!=nullptr, "Map 'cuda': cannot put function '" + f_.name() + "' on device(s) "
+                  + str(dv) + ": " + std::string(lib.last_error()));
     // FStats (timing.hpp:47-98): the whole call, and the device time of its three phases (they overlap chunk by chunk,
     // so the parts do not add up to the whole) plus the host time spent staging pageable buffers
     m->add_stat("cuda");
@@ -484,7 +515,7 @@ namespace casadi {
 
   void CudaMap::free_mem(void *mem) const {
     auto m = static_cast<CudaMapMemory*>(mem);
-    if (m->tape) cuda_lib().tape_destroy(m->tape);
+    if (m->tape) cuda_lib().multi_destroy(m->tape);
     delete m;
   }
 
@@ -496,6 +527,7 @@ namespace casadi {
                            const std::vector<bool>& reduce_out, void* mem) const {
     auto m = static_cast<CudaMapMemory*>(mem);
     CudaLib& lib = cuda_lib();
+    m->stats_available = true;  // F.stats() reports the timers of the last call (function_internal.cpp:3168-3175)
     m->fstats.at("cuda").tic();
     // Same contract as Map::eval_gen (map.cpp:141-157): instance i of input j is arg[j]+i*nnz_in(j);
     // null arg[j] reads as zero, null res[j] is not computed.  With reductions (MapSum::eval_gen, mapsum.cpp:154-186):
@@ -515,21 +547,25 @@ namespace casadi {
         r.push_back(&n_failed);
         red_out.push_back(1);
       }
-      flag = lib.map_eval_reduce_host(m->tape, n_*rep_, arg, get_ptr(r), reduce_in.empty() ? nullptr : get_ptr(red_in),
-                                      get_ptr(red_out));
+      flag = lib.multi_eval_host(m->tape, n_*rep_, arg, get_ptr(r), reduce_in.empty() ? nullptr : get_ptr(red_in),
+                                 get_ptr(red_out));
     } else {
-      flag = lib.map_eval_host(m->tape, n_*rep_, arg, res);
+      flag = lib.multi_eval_host(m->tape, n_*rep_, arg, res, nullptr, nullptr);
     }
     m->fstats.at("cuda").toc();
     {
-      double st[6] = {0, 0, 0, 0, 0, 0};
-      if (lib.last_eval_stats(m->tape, st) == 0) {
-        const char* names[4] = {"cuda_h2d", "cuda_kernel", "cuda_d2h", "cuda_stage"};
-        for (int k = 0; k < 4; ++k) {
-          FStats& fs = m->fstats.at(names[k]);
-          fs.n_call += 1;
-          fs.t_wall += 1e-3 * st[k];
-        }
+      // with several devices: the slowest device of each phase
+      double worst[4] = {0, 0, 0, 0};
+      for (int g = 0; g < lib.multi_size(m->tape); ++g) {
+        double st[6] = {0, 0, 0, 0, 0, 0};
+        if (lib.last_eval_stats(lib.multi_tape(m->tape, g), st) == 0)
+          for (int k = 0; k < 4; ++k) worst[k] = std::max(worst[k], st[k]);
+      }
+      const char* names[4] = {"cuda_h2d", "cuda_kernel", "cuda_d2h", "cuda_stage"};
+      for (int k = 0; k < 4; ++k) {
+        FStats& fs = m->fstats.at(names[k]);
+        fs.n_call += 1;
+        fs.t_wall += 1e-3 * worst[k];
       }
     }
     if (!flag && n_failed > 0) {

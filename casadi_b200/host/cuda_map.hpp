@@ -24,7 +24,7 @@ namespace casadi {
       checked-out memory, so concurrent evaluations on distinct memory objects do not share state
       (function_internal.hpp:184-194). */
   struct CASADI_EXPORT CudaMapMemory : public FunctionMemory {
-    void* tape;
+    void* tape;  // ccu_multi*: the compiled tape on every device of the map
     CudaMapMemory() : tape(nullptr) {}
   };
 
@@ -88,6 +88,7 @@ namespace casadi {
     bool flatten_;
     Tape tape_;
     int device_;
+    std::vector<int> devices_;  // CASADI_CUDA_DEVICES: the devices this map is sharded over (default: device_ alone)
     // MX functions that cannot be expanded (e.g. Linsol calls) are lowered node by node through the tape
     // builder of libcasadi_cuda.so; the recorded program lives in builder_ (one compiled tape per memory)
     void* builder_;

@@ -32,7 +32,7 @@ extern "C" {
 
 typedef long long ccu_int;
 
-#define CCU_ABI_VERSION 2
+#define CCU_ABI_VERSION 3
 #define CCU_LAYOUT_AOS 0
 #define CCU_LAYOUT_SOA 1
 #define CCU_MODE_INTERP 0 /* tape-interpreter kernel (always available)                                  */
@@ -42,7 +42,8 @@ typedef long long ccu_int;
 /* opaque handles */
 typedef struct ccu_tape ccu_tape;     /* a compiled SX instruction tape, resident on one device      */
 typedef struct ccu_linsol ccu_linsol; /* a symbolic LDL / QR factorisation shared by a whole batch   */
-typedef struct ccu_comm ccu_comm;     /* a set of NCCL communicators (reduce_out sums across GPUs)   */
+typedef struct ccu_comm ccu_comm;     /* NCCL communicator(s) of this process (reduce_out sums across GPUs) */
+typedef struct ccu_multi ccu_multi;   /* one tape replicated on several devices of this process + ccu_comm  */
 
 /* ------------------------------------------------------------------------------------------------
  * library
@@ -261,6 +262,46 @@ CCU_EXPORT int ccu_fp64_issue_rate(int device, double* ops_per_s);
  * a bit although the fast path did not flag the operands (must be 0), counts[1] = flagged (re-evaluated by the plain
  * operator in a kernel), counts[2] = checks.  Restates nothing of the reference: parity infrastructure of this library. */
 CCU_EXPORT int ccu_selftest_fastops(int device, long long n, unsigned long long seed, unsigned long long counts[3]);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU.  Instances are independent (map.cpp:147-155): the batch is cut into contiguous shards of
+ * whole 1024-instance reduction blocks, one per GPU, the tape is replicated, and NOTHING is exchanged for a plain
+ * map.  Only reduce_out communicates (HorzRepsum / MapSum sums, repmat.cpp:127-135, mapsum.cpp:170-184): every GPU
+ * writes the level-0 sums of its blocks at their global rows of a zero vector, ONE NCCL all-reduce over NVLink /
+ * NVSwitch merges the vectors (on the 64-bit patterns: the supports are disjoint, so the merge is exact down to -0.0
+ * and NaN payloads) and the level-1 tree runs on the merged vector -- the sums have the bits of a single-GPU run for
+ * any number of GPUs.  libnccl is bound at run time (CCU_NCCL_LIB, libnccl.so.2); single-GPU use never loads it.
+ * ---------------------------------------------------------------------------------------------- */
+/* 1 when libnccl can be loaded in this process (else 0 and ccu_last_error says why) */
+CCU_EXPORT int ccu_comm_available(void);
+CCU_EXPORT int ccu_comm_nccl_version(void);
+/* one process driving several devices: ncclCommInitAll over devices[0..n) (devices == NULL: 0..n-1) */
+CCU_EXPORT ccu_comm* ccu_comm_create_all(int n_devices, const int* devices);
+/* one rank of a multi-process job: id from ccu_comm_unique_id on one rank, distributed by the host (ncclCommInitRank) */
+CCU_EXPORT int ccu_comm_unique_id(unsigned char id[128]);
+CCU_EXPORT ccu_comm* ccu_comm_create_rank(const unsigned char id[128], int rank, int n_ranks, int device);
+CCU_EXPORT void ccu_comm_destroy(ccu_comm* c);
+CCU_EXPORT int ccu_comm_size(const ccu_comm* c);
+/* In-place all-reduce of the zero-padded block-sum vectors d_part[k][0..count) -- one per LOCAL device of the
+ * communicator, on streams[k] (NULL: default streams) -- as produced by ccu_map_eval_shard_device; follow with
+ * ccu_reduce_tree_device.  Asynchronous on the streams. */
+CCU_EXPORT int ccu_comm_allreduce_block_sums(ccu_comm* c, double* const* d_part, ccu_int count, void* const* streams);
+
+/* `f.map(N, "cuda")` over several devices of ONE process (what CudaMap builds for CASADI_CUDA_DEVICES=all|0,1,..):
+ * replicas of the tape of ccu_tape_create / ccu_builder_finish on devices[0..n) and, for n > 1, their communicator. */
+CCU_EXPORT ccu_multi* ccu_multi_create(ccu_int n_instr, const int* op, const int* i0, const int* i1, const int* i2,
+                                       const double* d, ccu_int sz_w, ccu_int n_in, const ccu_int* nnz_in, ccu_int n_out,
+                                       const ccu_int* nnz_out, int n_devices, const int* devices);
+CCU_EXPORT ccu_multi* ccu_builder_finish_multi(ccu_builder* b, ccu_int n_in, const ccu_int* nnz_in, ccu_int n_out,
+                                               const ccu_int* nnz_out, int n_devices, const int* devices);
+CCU_EXPORT void ccu_multi_destroy(ccu_multi* m);
+CCU_EXPORT int ccu_multi_size(const ccu_multi* m);
+CCU_EXPORT ccu_tape* ccu_multi_tape(ccu_multi* m, int k); /* replica k (owned by m) */
+/* ccu_map_eval_reduce_host over all devices of m: device g evaluates instances [g*N/G, (g+1)*N/G) (whole reduction
+ * blocks) through its own chunked host pipeline, concurrently; reduced outputs are combined by NCCL as described
+ * above.  reduce_in / reduce_out may be NULL (plain map).  Same arguments and error behaviour as the single-device call. */
+CCU_EXPORT int ccu_multi_eval_host(ccu_multi* m, ccu_int N, const double* const* arg, double* const* res,
+                                   const int* reduce_in, const int* reduce_out);
 
 /* ------------------------------------------------------------------------------------------------
  * Device memory helpers (so a C or C++ host needs no CUDA headers)

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), "libcasadi_cuda.so does not export %s" % name
     assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
-    assert L.ccu_abi_version() == 2
+    assert L.ccu_abi_version() == 3
 
 
 def emulate(tape_name, case_name, S, nmax=64, sched=None):

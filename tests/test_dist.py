@@ -116,3 +116,56 @@ def test_shard_entry_point_reproduces_single_gpu_reduction_bits():
     torch.cuda.synchronize()
     for j in range(2):
         assert_bit_equal(outs[j].cpu().numpy(), ref[j], "ShardedCudaMap out%d" % j)
+
+
+def _n_gpus():
+    try:
+        from casadi_b200 import capi
+        return capi.lib().ccu_device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+def test_single_process_multi_device_map_has_single_gpu_bits():
+    """ccu_multi (what CudaMap builds for CASADI_CUDA_DEVICES): the batch sharded over all visible devices of this
+    process, reduce_out block sums merged by the library's NCCL all-reduce -- every output bit-identical to the
+    single-device evaluation, for plain maps and for reductions (repmat.cpp:127-135 / mapsum.cpp:170-184 semantics)."""
+    G = _n_gpus()
+    if G < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    from casadi_b200 import CudaMap, CudaMultiMap, CudaTape, load_case, load_tape
+    tape, case = load_tape("mc"), load_case("mc")
+    P, reps = case["N"], 41
+    N = P * reps - 5
+    ins = [np.tile(a, reps)[:N * int(n)] for a, n in zip(case["in"], tape["nnz_in"])]
+    ins[0][::3] *= -0.0  # signed zeros survive the merge (the all-reduce runs on the bit patterns)
+    one = CudaTape(tape, device=0)
+    ref_plain = CudaMap(one, N)(ins)
+    ref_red = CudaMap(one, N, reduce_out=[1, 1])(ins)
+    ref_rin = CudaMap(one, N, reduce_in=[1, 0], reduce_out=[0, 1])([ins[0][:4], ins[1]])
+    for devs in ([0, 1], list(range(G))):
+        mm = CudaMultiMap(tape, N, devs)
+        for j, (a, b) in enumerate(zip(mm(ins), ref_plain)):
+            assert_bit_equal(a, b, "plain map on devices %s out%d" % (devs, j))
+        mr = CudaMultiMap(tape, N, devs, reduce_out=[1, 1])
+        for j, (a, b) in enumerate(zip(mr(ins), ref_red)):
+            assert_bit_equal(a, b, "reduce_out on devices %s out%d" % (devs, j))
+        mi = CudaMultiMap(tape, N, devs, reduce_in=[1, 0], reduce_out=[0, 1])
+        for j, (a, b) in enumerate(zip(mi([ins[0][:4], ins[1]]), ref_rin)):
+            assert_bit_equal(a, b, "reduce_in + reduce_out on devices %s out%d" % (devs, j))
+
+
+@pytest.mark.gpu
+def test_cuda_map_plugin_on_all_devices():
+    """The C++ CudaMap inside the relinked reference library with CASADI_CUDA_DEVICES=all: the whole integration
+    suite (maps, reductions, MapSum, Linsol lowering, derivatives) against the reference's serial map."""
+    if _n_gpus() < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "integration", "_build", "bin", "test_cuda_map")
+    assert os.path.exists(exe)
+    env = dict(os.environ, CASADI_CUDA_LIB=os.path.join(ROOT, "casadi_b200", "lib", "libcasadi_cuda.so"), CASADI_CUDA_DEVICES="all")
+    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "integration ok" in r.stdout
