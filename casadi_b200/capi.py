@@ -63,6 +63,7 @@ SYMBOLS = {
     "ccu_multi_size": (ctypes.c_int, [c_vp]),
     "ccu_multi_tape": (c_vp, [c_vp, ctypes.c_int]),
     "ccu_multi_eval_host": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_i_p, c_i_p]),
+    "ccu_multi_eval_host_grouped": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_i_p, c_i_p, c_i_p, c_i_p]),
     "ccu_builder_create": (c_vp, []),
     "ccu_builder_destroy": (None, [c_vp]),
     "ccu_builder_const": (c_ll, [c_vp, ctypes.c_double]),
@@ -103,7 +104,7 @@ class TapeInfo(ctypes.Structure):
                                     "max_live", "grid", "ctas_per_sm", "mode", "jit_segments",
                                     "jit_scratch_slots", "jit_tile", "jit_compile_ms", "jit_cross_loads",
                                     "jit_cross_stores", "jit_max_regs", "jit_cache_hits", "jit_threads",
-                                    "jit_schedule", "jit_schedule_ms", "jit_chained")]
+                                    "jit_schedule", "jit_schedule_ms", "jit_chained", "cse_removed")]
 
 
 _lib = None

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -94,24 +95,32 @@ class CopyPool {
   static CopyPool& get() { static CopyPool pool; return pool; }
   void copy(void* dst, const void* src, size_t bytes) {
     if (bytes == 0) return;
-    const size_t kSlice = 2u << 20;
     if (workers_.empty() || bytes <= kSlice) { std::memcpy(dst, src, bytes); return; }
+    auto job = std::make_shared<Job>();
+    job->dst = static_cast<char*>(dst); job->src = static_cast<const char*>(src); job->bytes = bytes;
+    job->slices = (bytes + kSlice - 1) / kSlice;
     std::lock_guard<std::mutex> one(run_mu_);  // one copy at a time
     {
       std::lock_guard<std::mutex> lk(mu_);
-      dst_ = static_cast<char*>(dst); src_ = static_cast<const char*>(src); bytes_ = bytes;
-      slices_ = (bytes + kSlice - 1) / kSlice;
-      next_.store(0); done_.store(0);
+      cur_ = job;
       ++epoch_;
     }
     cv_.notify_all();
-    work(kSlice);
+    work(*job);
     std::unique_lock<std::mutex> lk(mu_);
-    cv_done_.wait(lk, [&] { return done_.load() == slices_; });
+    cv_done_.wait(lk, [&] { return job->done.load() == job->slices; });
   }
   int threads() const { return static_cast<int>(workers_.size()) + 1; }
 
  private:
+  static constexpr size_t kSlice = 2u << 20;
+  // the state of one copy; a worker that is late leaving a finished job only ever touches that job's counters
+  struct Job {
+    char* dst = nullptr;
+    const char* src = nullptr;
+    size_t bytes = 0, slices = 0;
+    std::atomic<size_t> next{0}, done{0};
+  };
   CopyPool() {
     int n = static_cast<int>(std::thread::hardware_concurrency()) / 2;
     n = std::max(1, std::min(8, n));
@@ -119,33 +128,32 @@ class CopyPool {
     for (int i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
     for (auto& t : workers_) t.detach();  // workers live as long as the process
   }
-  void work(size_t slice) {
+  void work(Job& j) {
     for (;;) {
-      const size_t k = next_.fetch_add(1);
-      if (k >= slices_) return;
-      const size_t off = k * slice, len = std::min(slice, bytes_ - off);
-      std::memcpy(dst_ + off, src_ + off, len);
-      if (done_.fetch_add(1) + 1 == slices_) { std::lock_guard<std::mutex> lk(mu_); cv_done_.notify_all(); }
+      const size_t k = j.next.fetch_add(1);
+      if (k >= j.slices) return;
+      const size_t off = k * kSlice, len = std::min(kSlice, j.bytes - off);
+      std::memcpy(j.dst + off, j.src + off, len);
+      if (j.done.fetch_add(1) + 1 == j.slices) { std::lock_guard<std::mutex> lk(mu_); cv_done_.notify_all(); }
     }
   }
   void loop() {
     unsigned long long seen = 0;
     for (;;) {
+      std::shared_ptr<Job> job;
       {
         std::unique_lock<std::mutex> lk(mu_);
         cv_.wait(lk, [&] { return epoch_ != seen; });
         seen = epoch_;
+        job = cur_;
       }
-      work(2u << 20);
+      if (job) work(*job);
     }
   }
   std::vector<std::thread> workers_;
   std::mutex mu_, run_mu_;
   std::condition_variable cv_, cv_done_;
-  char* dst_ = nullptr;
-  const char* src_ = nullptr;
-  size_t bytes_ = 0, slices_ = 0;
-  std::atomic<size_t> next_{0}, done_{0};
+  std::shared_ptr<Job> cur_;
   unsigned long long epoch_ = 0;
 };
 
@@ -194,7 +202,7 @@ struct ccu_tape {
   std::vector<double> d;
   long long sz_w = 0;
   std::vector<long long> nnz_in, nnz_out;
-  long long max_live = 0, flops = 0;
+  long long max_live = 0, flops = 0, cse_removed = 0;
   // compiled program + plan
   ccu::Program prog;
   ccu::LaunchPlan plan;
@@ -432,7 +440,7 @@ ccu_tape* ccu_tape_create(ccu_int n_instr, const int* op, const int* i0, const i
   const char* noacc = getenv("CCU_NO_ACC");
   t->use_acc = !(noacc && noacc[0] == '1');
   std::string err;
-  if (!ccu::analyse_tape(t->source(), &t->max_live, &t->flops, &err)) {
+  if (!ccu::analyse_tape(t->source(), &t->max_live, &t->flops, &err, &t->cse_removed)) {
     fail("invalid tape: %s", err.c_str());
     delete t;
     return nullptr;
@@ -525,6 +533,7 @@ int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info) {
   info->grid = t->plan.grid;
   info->ctas_per_sm = t->plan.ctas_per_sm;
   info->mode = t->mode;
+  info->cse_removed = t->cse_removed;
   if (t->jit_built) {
     info->jit_segments = t->jit.segments;
     info->jit_chained = t->jit.chain ? 1 : 0;
@@ -746,9 +755,14 @@ int ccu_reduce_tree_device(int device, double* d_part, ccu_int N_global, ccu_int
 // (g_off, N_glob): position of these N instances inside the whole batch when the batch is sharded over several devices
 // (ccu_multi); the block sums of reduced outputs are then written at their GLOBAL rows of d_part and the cross-device
 // combine + level-1 tree is left to the caller (finish_reduce == false).
+// in_groups / out_groups (may be NULL): input / output j of an instance is G_j pieces of nnz/G_j doubles and the caller's
+// buffer is PIECE-major -- piece d of instance k at arg[j] + (d*N_glob + k) * (nnz/G_j) -- the layout in which the
+// reference hands the nfwd (nadj) seed / sensitivity blocks to a derivative map (map.cpp:231-264, 285-318: the
+// GetNonzeros column permutations around df.map(n)); the permutation is folded into the chunk copies here.  For grouped
+// buffers arg[j] / res[j] are the UNSHIFTED bases even for a shard (g_off is added here).
 static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res,
                             const int* reduce_in, const int* reduce_out, long long g_off, long long N_glob,
-                            bool finish_reduce) {
+                            bool finish_reduce, const int* in_groups, const int* out_groups) {
   const size_t n_in = t->nnz_in.size(), n_out = t->nnz_out.size();
   HostPipe& hp = t->pipe;
   cudaStream_t s_h2d = hp.s[0], s_cmp = hp.s[1], s_d2h = hp.s[2];
@@ -762,6 +776,21 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
   const long long blk_off = g_off / ccu::kReduceBlock;
   auto is_rin = [&](size_t j) { return reduce_in && reduce_in[j]; };
   auto is_rout = [&](size_t j) { return reduce_out && reduce_out[j]; };
+  auto gin = [&](size_t j) { return (in_groups && in_groups[j] > 1) ? in_groups[j] : 1; };
+  auto gout = [&](size_t j) { return (out_groups && out_groups[j] > 1) ? out_groups[j] : 1; };
+  for (size_t j = 0; j < n_in; ++j)
+    if (gin(j) > 1 && (t->nnz_in[j] % gin(j) != 0 || is_rin(j))) return fail("input %zu: invalid piece count %d", j, gin(j));
+  for (size_t j = 0; j < n_out; ++j)
+    if (gout(j) > 1 && (t->nnz_out[j] % gout(j) != 0 || is_rout(j))) return fail("output %zu: invalid piece count %d", j, gout(j));
+  // caller address of piece d of the chunk starting at local instance i0 (ungrouped: d = 0, the shard-shifted pointer)
+  auto in_src = [&](size_t j, int d, long long i0) {
+    const long long m = t->nnz_in[j] / gin(j);
+    return gin(j) > 1 ? arg[j] + (d * N_glob + g_off + i0) * m : arg[j] + i0 * m;
+  };
+  auto out_dst = [&](size_t j, int d, long long i0) {
+    const long long m = t->nnz_out[j] / gout(j);
+    return gout(j) > 1 ? res[j] + (d * N_glob + g_off + i0) * m : res[j] + i0 * m;
+  };
   // which caller buffers need pinned staging
   std::vector<char> stage_in(n_in, 0), stage_out(n_out, 0);
   const char* force = getenv("CCU_HOST_STAGING");  // "0": never stage (driver-staged copies), "1": always
@@ -808,9 +837,12 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
     const auto t0 = std::chrono::steady_clock::now();
     for (size_t j = 0; j < n_out; ++j) {
       if (!stage_out[j]) continue;
-      const size_t bytes = static_cast<size_t>(n) * t->nnz_out[j] * 8;
-      pool.copy(res[j] + i0 * t->nnz_out[j], hp.out_pin[b][j].p, bytes);
-      t->st_staged_bytes += static_cast<double>(bytes);
+      const long long m = t->nnz_out[j] / gout(j);
+      for (int d = 0; d < gout(j); ++d) {
+        const size_t bytes = static_cast<size_t>(n) * m * 8;
+        pool.copy(out_dst(j, d, i0), hp.out_pin[b][j].p + static_cast<size_t>(d) * n * m, bytes);
+        t->st_staged_bytes += static_cast<double>(bytes);
+      }
     }
     stage_ms(t0);
     return 0;
@@ -831,9 +863,12 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
         for (size_t j = 0; j < n_in; ++j) {
           if (!stage_in[j]) continue;
           if (hp.in_pin[b][j].ensure(static_cast<size_t>(t->nnz_in[j]) * C)) return 1;
-          const size_t bytes = static_cast<size_t>(n) * t->nnz_in[j] * 8;
-          pool.copy(hp.in_pin[b][j].p, arg[j] + i0 * t->nnz_in[j], bytes);
-          t->st_staged_bytes += static_cast<double>(bytes);
+          const long long m = t->nnz_in[j] / gin(j);
+          for (int d = 0; d < gin(j); ++d) {
+            const size_t bytes = static_cast<size_t>(n) * m * 8;
+            pool.copy(hp.in_pin[b][j].p + static_cast<size_t>(d) * n * m, in_src(j, d, i0), bytes);
+            t->st_staged_bytes += static_cast<double>(bytes);
+          }
         }
         stage_ms(t0);
       }
@@ -846,8 +881,15 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
       if (is_rin(j)) { d_arg[j] = hp.bcast[j].p; continue; }
       const size_t cnt = static_cast<size_t>(t->nnz_in[j]) * C;
       if (hp.in_aos[b][j].ensure(cnt) || hp.in_soa[b][j].ensure(cnt)) return 1;
-      const double* src = stage_in[j] ? hp.in_pin[b][j].p : arg[j] + i0 * t->nnz_in[j];
-      CCU_CUDA(cudaMemcpyAsync(hp.in_aos[b][j].p, src, static_cast<size_t>(n) * t->nnz_in[j] * 8, cudaMemcpyHostToDevice, s_h2d));
+      if (stage_in[j] || gin(j) == 1) {
+        const double* src = stage_in[j] ? hp.in_pin[b][j].p : in_src(j, 0, i0);
+        CCU_CUDA(cudaMemcpyAsync(hp.in_aos[b][j].p, src, static_cast<size_t>(n) * t->nnz_in[j] * 8, cudaMemcpyHostToDevice, s_h2d));
+      } else {
+        const long long m = t->nnz_in[j] / gin(j);
+        for (int d = 0; d < gin(j); ++d)
+          CCU_CUDA(cudaMemcpyAsync(hp.in_aos[b][j].p + static_cast<size_t>(d) * n * m, in_src(j, d, i0), static_cast<size_t>(n) * m * 8,
+                                   cudaMemcpyHostToDevice, s_h2d));
+      }
       d_arg[j] = hp.in_soa[b][j].p;
     }
     CCU_CUDA(cudaEventRecord(hp.tev[b][1], s_h2d));
@@ -858,8 +900,13 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
     CCU_CUDA(cudaEventRecord(hp.tev[b][2], s_cmp));
     for (size_t j = 0; j < n_in; ++j) {
       if (!arg[j] || t->nnz_in[j] == 0 || is_rin(j)) continue;
-      CCU_CUDA(ccu::launch_aos_to_soa(hp.in_aos[b][j].p, hp.in_soa[b][j].p, n, static_cast<int>(t->nnz_in[j]), n, s_cmp));
-      g_launches++;
+      // (piece d of a grouped input is an AoS block of its own: rows [d*m, (d+1)*m) of the SoA operand)
+      const long long m = t->nnz_in[j] / gin(j);
+      for (int d = 0; d < gin(j); ++d) {
+        CCU_CUDA(ccu::launch_aos_to_soa(hp.in_aos[b][j].p + static_cast<size_t>(d) * n * m, hp.in_soa[b][j].p + static_cast<size_t>(d) * m * n,
+                                        n, static_cast<int>(m), n, s_cmp));
+        g_launches++;
+      }
     }
     for (size_t j = 0; j < n_out; ++j) {
       if (!res[j] || t->nnz_out[j] == 0) continue;
@@ -877,10 +924,15 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
       const int nnz = static_cast<int>(t->nnz_out[j]);
       if (is_rout(j)) {
         CCU_CUDA(ccu::launch_block_sums(d_res[j], 1, n, n, nnz, t->d_part[j].p + (blk_off + i0 / ccu::kReduceBlock) * nnz, s_cmp));
+        g_launches++;
       } else {
-        CCU_CUDA(ccu::launch_soa_to_aos(d_res[j], hp.out_aos[b][j].p, n, nnz, n, s_cmp));
+        const long long m = nnz / gout(j);
+        for (int d = 0; d < gout(j); ++d) {
+          CCU_CUDA(ccu::launch_soa_to_aos(d_res[j] + static_cast<size_t>(d) * m * n, hp.out_aos[b][j].p + static_cast<size_t>(d) * n * m, n,
+                                          static_cast<int>(m), n, s_cmp));
+          g_launches++;
+        }
       }
-      g_launches++;
     }
     CCU_CUDA(cudaEventRecord(hp.tev[b][3], s_cmp));
     CCU_CUDA(cudaEventRecord(hp.ev[b][1], s_cmp));
@@ -889,8 +941,15 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
     CCU_CUDA(cudaEventRecord(hp.tev[b][4], s_d2h));
     for (size_t j = 0; j < n_out; ++j) {
       if (!d_res[j] || is_rout(j)) continue;
-      double* dst = stage_out[j] ? hp.out_pin[b][j].p : res[j] + i0 * t->nnz_out[j];
-      CCU_CUDA(cudaMemcpyAsync(dst, hp.out_aos[b][j].p, static_cast<size_t>(n) * t->nnz_out[j] * 8, cudaMemcpyDeviceToHost, s_d2h));
+      if (stage_out[j] || gout(j) == 1) {
+        double* dst = stage_out[j] ? hp.out_pin[b][j].p : out_dst(j, 0, i0);
+        CCU_CUDA(cudaMemcpyAsync(dst, hp.out_aos[b][j].p, static_cast<size_t>(n) * t->nnz_out[j] * 8, cudaMemcpyDeviceToHost, s_d2h));
+      } else {
+        const long long m = t->nnz_out[j] / gout(j);
+        for (int d = 0; d < gout(j); ++d)
+          CCU_CUDA(cudaMemcpyAsync(out_dst(j, d, i0), hp.out_aos[b][j].p + static_cast<size_t>(d) * n * m, static_cast<size_t>(n) * m * 8,
+                                   cudaMemcpyDeviceToHost, s_d2h));
+      }
     }
     CCU_CUDA(cudaEventRecord(hp.tev[b][5], s_d2h));
     CCU_CUDA(cudaEventRecord(hp.ev[b][2], s_d2h));
@@ -917,7 +976,7 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
 
 static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res,
                           const int* reduce_in, const int* reduce_out, long long g_off = 0, long long N_glob = -1,
-                          bool finish_reduce = true) {
+                          bool finish_reduce = true, const int* in_groups = nullptr, const int* out_groups = nullptr) {
   if (N_glob < 0) N_glob = N;
   if (check_eval_args(t, N)) return 1;
   if (!arg || !res) return fail("null argument / result array");
@@ -940,7 +999,7 @@ static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, doub
   t->st_h2d_ms = t->st_kernel_ms = t->st_d2h_ms = t->st_stage_ms = t->st_wall_ms = t->st_staged_bytes = 0;
   hp.tev_used[0] = hp.tev_used[1] = false;
   const auto t0 = std::chrono::steady_clock::now();
-  int rc = eval_host_chunks(t, N, arg, res, reduce_in, reduce_out, g_off, N_glob, finish_reduce);
+  int rc = eval_host_chunks(t, N, arg, res, reduce_in, reduce_out, g_off, N_glob, finish_reduce, in_groups, out_groups);
   const std::string first_error = rc ? g_err : std::string();
   // Whatever happened, nothing may still read the caller's inputs or write the caller's outputs after the return
   cudaError_t e0 = cudaStreamSynchronize(hp.s[0]), e1 = cudaStreamSynchronize(hp.s[1]), e2 = cudaStreamSynchronize(hp.s[2]);
@@ -1027,11 +1086,26 @@ struct ccu_multi {
   ccu_comm* comm = nullptr;      // null for a single device
 };
 
+// Communicators of a device set are created once per process and shared by every map on that set (ncclCommInitAll takes
+// seconds; a CasADi program creates many maps): kept until the process ends, used by one evaluation at a time.
+static std::mutex g_comm_mutex;
+static std::vector<std::pair<std::vector<int>, ccu_comm*>> g_comm_cache;
+static std::mutex g_comm_use;  // a shared communicator carries one collective at a time
+
+static ccu_comm* shared_comm(int n_devices, const int* devices) {
+  std::vector<int> key(devices, devices + n_devices);
+  std::lock_guard<std::mutex> lk(g_comm_mutex);
+  for (auto& e : g_comm_cache) if (e.first == key) return e.second;
+  ccu_comm* c = ccu_comm_create_all(n_devices, devices);
+  if (c) g_comm_cache.emplace_back(key, c);
+  return c;
+}
+
 static ccu_multi* multi_finish(std::vector<ccu_tape*>& tapes, int n_devices, const int* devices) {
   ccu_multi* m = new ccu_multi();
   m->tapes = tapes;
   if (n_devices > 1) {
-    m->comm = ccu_comm_create_all(n_devices, devices);
+    m->comm = shared_comm(n_devices, devices);
     if (!m->comm) {
       const std::string e = g_err;
       for (ccu_tape* t : tapes) ccu_tape_destroy(t);
@@ -1072,7 +1146,7 @@ ccu_multi* ccu_builder_finish_multi(ccu_builder* b, ccu_int n_in, const ccu_int*
 void ccu_multi_destroy(ccu_multi* m) {
   if (!m) return;
   for (ccu_tape* t : m->tapes) ccu_tape_destroy(t);
-  ccu_comm_destroy(m->comm);
+  // (the communicator is shared: shared_comm)
   delete m;
 }
 
@@ -1086,9 +1160,14 @@ ccu_tape* ccu_multi_tape(ccu_multi* m, int k) {
 // level-1 tree on device 0 (HorzRepsum / MapSum semantics, repmat.cpp:127-135, mapsum.cpp:170-184).
 int ccu_multi_eval_host(ccu_multi* m, ccu_int N, const double* const* arg, double* const* res, const int* reduce_in,
                         const int* reduce_out) {
+  return ccu_multi_eval_host_grouped(m, N, arg, res, reduce_in, reduce_out, nullptr, nullptr);
+}
+
+int ccu_multi_eval_host_grouped(ccu_multi* m, ccu_int N, const double* const* arg, double* const* res, const int* reduce_in,
+                                const int* reduce_out, const int* in_groups, const int* out_groups) {
   if (!m || m->tapes.empty()) return fail("null multi-device map");
   const int G = static_cast<int>(m->tapes.size());
-  if (G == 1) return eval_host_impl(m->tapes[0], N, arg, res, reduce_in, reduce_out);
+  if (G == 1) return eval_host_impl(m->tapes[0], N, arg, res, reduce_in, reduce_out, 0, N, true, in_groups, out_groups);
   if (check_eval_args(m->tapes[0], N)) return 1;
   ccu_tape* t0 = m->tapes[0];
   const size_t n_in = t0->nnz_in.size(), n_out = t0->nnz_out.size();
@@ -1109,11 +1188,12 @@ int ccu_multi_eval_host(ccu_multi* m, ccu_int N, const double* const* arg, doubl
       const long long i0 = off[g], n = off[g + 1] - off[g];
       std::vector<const double*> a(n_in, nullptr);
       std::vector<double*> r(n_out, nullptr);
+      // (grouped buffers keep their base: the piece-major layout is addressed from the start of the whole batch)
       for (size_t j = 0; j < n_in; ++j)
-        a[j] = arg[j] ? ((reduce_in && reduce_in[j]) ? arg[j] : arg[j] + i0 * t0->nnz_in[j]) : nullptr;
+        a[j] = arg[j] ? (((reduce_in && reduce_in[j]) || (in_groups && in_groups[j] > 1)) ? arg[j] : arg[j] + i0 * t0->nnz_in[j]) : nullptr;
       for (size_t j = 0; j < n_out; ++j)
-        r[j] = res[j] ? ((reduce_out && reduce_out[j]) ? res[j] : res[j] + i0 * t0->nnz_out[j]) : nullptr;
-      rcs[g] = eval_host_impl(m->tapes[g], n, a.data(), r.data(), reduce_in, reduce_out, i0, N, /*finish_reduce=*/false);
+        r[j] = res[j] ? (((reduce_out && reduce_out[j]) || (out_groups && out_groups[j] > 1)) ? res[j] : res[j] + i0 * t0->nnz_out[j]) : nullptr;
+      rcs[g] = eval_host_impl(m->tapes[g], n, a.data(), r.data(), reduce_in, reduce_out, i0, N, /*finish_reduce=*/false, in_groups, out_groups);
       if (rcs[g]) errs[g] = g_err;
     });
   }
@@ -1126,6 +1206,7 @@ int ccu_multi_eval_host(ccu_multi* m, ccu_int N, const double* const* arg, doubl
     std::vector<double*> bufs(G);
     std::vector<void*> streams(G);
     for (int g = 0; g < G; ++g) { bufs[g] = m->tapes[g]->d_part[j].p; streams[g] = m->tapes[g]->pipe.s[1]; }
+    std::lock_guard<std::mutex> use(g_comm_use);
     if (ccu_comm_allreduce_block_sums(m->comm, bufs.data(), std::max<long long>(blocks, 1) * nnz, streams.data())) return 1;
     CCU_CUDA(cudaSetDevice(t0->device));
     HostPipe& hp = t0->pipe;

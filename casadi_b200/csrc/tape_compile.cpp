@@ -12,8 +12,10 @@
 #include "tape_compile.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <set>
+#include <unordered_map>
 
 #include "ccu_isa.h"
 #include "tape_schedule.hpp"
@@ -89,7 +91,7 @@ bool map_op(int rop, int* dop, int* nop) {
 
 }  // namespace
 
-bool build_graph(const TapeSource& s, std::vector<Node>* nodes, long long* flops, std::string* err) {
+bool build_graph(const TapeSource& s, std::vector<Node>* nodes, long long* flops, std::string* err, long long* removed) {
   const long long n = s.n_instr;
   if (n < 0 || s.sz_w < 0) { *err = "negative tape size"; return false; }
   if (n > 0 && (!s.op || !s.i0 || !s.i1 || !s.i2 || !s.d)) { *err = "null tape arrays"; return false; }
@@ -151,12 +153,67 @@ bool build_graph(const TapeSource& s, std::vector<Node>* nodes, long long* flops
     }
     nodes->push_back(nd);
   }
+  // Value numbering: an instruction whose operation and operand VALUES equal those of an earlier one produces the same
+  // bits (every operation is a pure function of its operands), so it is dropped and its readers use the earlier value.
+  // The reference's AD emits the derivative's sin/cos, quotients and products next to identical primal ones (quadrotor
+  // Jacobian: 9 100 of 76 911 instructions, among them 480 of its 960 sin/cos; rocket hess_lag: 4 596 of 20 321 incl.
+  // 1 198 divisions).  ADD and MUL are matched in either operand order (IEEE addition and multiplication commute bit for
+  // bit); fmin/fmax are not (their +-0 ties return the first operand).  `flops` stays the reference's count.
+  static const bool cse_on = [] { const char* e = getenv("CCU_CSE"); return !(e && e[0] == '0'); }();
+  if (removed) *removed = 0;
+  if (cse_on && !nodes->empty()) {
+    struct Key {
+      uint64_t k0, k1;
+      bool operator==(const Key& o) const { return k0 == o.k0 && k1 == o.k1; }
+    };
+    struct KeyHash {
+      size_t operator()(const Key& k) const { return static_cast<size_t>((k.k0 * 0x9e3779b97f4a7c15ull) ^ (k.k1 + 0x7f4a7c15ull + (k.k0 << 6))); }
+    };
+    std::unordered_map<Key, int, KeyHash> seen;
+    seen.reserve(nodes->size() * 2);
+    const int m = static_cast<int>(nodes->size());
+    std::vector<int> rep(m);      // node -> representative (old index)
+    std::vector<int> newid(m, -1);
+    std::vector<Node> kept;
+    kept.reserve(m);
+    long long dropped = 0;
+    for (int k = 0; k < m; ++k) {
+      Node nd = (*nodes)[k];
+      rep[k] = k;
+      if (nd.a >= 0) nd.a = newid[rep[nd.a]];
+      if (nd.b >= 0) nd.b = newid[rep[nd.b]];
+      if (nd.kind == K_OUTPUT) { newid[k] = static_cast<int>(kept.size()); kept.push_back(nd); continue; }
+      Key key;
+      if (nd.kind == K_CONST) {
+        uint64_t bits;
+        std::memcpy(&bits, &nd.c, 8);
+        key = {(1ull << 62) | 1, bits};
+      } else if (nd.kind == K_INPUT) {
+        key = {(1ull << 62) | 2, (static_cast<uint64_t>(static_cast<uint32_t>(nd.idx)) << 32) | static_cast<uint32_t>(nd.nz)};
+      } else {
+        int a = nd.a, b = nd.b;
+        if ((nd.dop == D_ADD || nd.dop == D_MUL) && b >= 0 && b < a) std::swap(a, b);
+        key = {static_cast<uint64_t>(nd.dop), (static_cast<uint64_t>(static_cast<uint32_t>(a)) << 32) | static_cast<uint32_t>(b)};
+      }
+      auto it = seen.find(key);
+      if (it != seen.end()) {
+        rep[k] = it->second;
+        dropped += nd.kind == K_ARITH;
+        continue;
+      }
+      seen.emplace(key, k);
+      newid[k] = static_cast<int>(kept.size());
+      kept.push_back(nd);
+    }
+    nodes->swap(kept);
+    if (removed) *removed = dropped;
+  }
   return true;
 }
 
-bool analyse_tape(const TapeSource& src, long long* max_live, long long* flops, std::string* err) {
+bool analyse_tape(const TapeSource& src, long long* max_live, long long* flops, std::string* err, long long* removed) {
   std::vector<Node> nodes;
-  if (!build_graph(src, &nodes, flops, err)) return false;
+  if (!build_graph(src, &nodes, flops, err, removed)) return false;
   const int n = static_cast<int>(nodes.size());
   std::vector<int> last(n);
   for (int k = 0; k < n; ++k) last[k] = k;

@@ -46,12 +46,14 @@ struct Node {
   int idx = 0, nz = 0;  // INPUT: input index / nonzero; OUTPUT: output index / nonzero
   double c = 0;         // CONST literal
 };
-// Validates the tape and builds the graph; `flops` = arithmetic instructions.
-bool build_graph(const TapeSource& s, std::vector<Node>* nodes, long long* flops, std::string* err);
+// Validates the tape and builds the graph; `flops` = arithmetic instructions of the tape.  Instructions that
+// repeat an earlier one on the same operand values are dropped (value numbering; CCU_CSE=0 keeps them): `removed` = how
+// many arithmetic instructions that saved.
+bool build_graph(const TapeSource& s, std::vector<Node>* nodes, long long* flops, std::string* err, long long* removed = nullptr);
 
 // Validates the tape (throws nothing; returns false and sets err) and computes the number of
 // simultaneously live values -- what an allocation without spills needs.
-bool analyse_tape(const TapeSource& src, long long* max_live, long long* flops, std::string* err);
+bool analyse_tape(const TapeSource& src, long long* max_live, long long* flops, std::string* err, long long* removed = nullptr);
 
 bool compile_tape(const TapeSource& src, const CompileOptions& opt, Program* out, std::string* err);
 

@@ -144,6 +144,7 @@ struct Bisector {
   const ScheduleOptions& opt;
   int n;
   std::vector<int> cstart, cons;      // distinct consumers of every arithmetic value
+  std::vector<int> partner;           // sin(x) <-> cos(x) of the same operand (kept in one piece: jit.cpp fuses them)
   std::vector<std::atomic<int>> lo;   // node -> start of its current interval
   std::vector<int> out;               // items in final order (written by position)
   std::vector<PieceRec> pieces;       // every piece of the recursion (any order; sorted at the end)
@@ -175,6 +176,20 @@ struct Bisector {
     std::vector<int> fill(cstart.begin(), cstart.end() - 1);
     for (int k = 0; k < n; ++k) each_operand(k, [&](int u) { cons[fill[u]++] = k; });
     for (auto& x : lo) x.store(0, std::memory_order_relaxed);
+    // sin / cos pairs on one operand: the specialised kernels evaluate a pair with ONE argument reduction when both
+    // are in the same kernel (238 of the quadrotor Jacobian's 480 pairs were split by the cuts before they were tied)
+    partner.assign(n, -1);
+    if (opt.tie_sincos) {
+      std::vector<int> first_sin(n, -1), first_cos(n, -1);
+      for (int k = 0; k < n; ++k) {
+        const Node& nd = N[k];
+        if (nd.kind != K_ARITH || nd.a < 0) continue;
+        if (nd.dop == D_SIN && first_sin[nd.a] < 0) first_sin[nd.a] = k;
+        if (nd.dop == D_COS && first_cos[nd.a] < 0) first_cos[nd.a] = k;
+      }
+      for (int v = 0; v < n; ++v)
+        if (first_sin[v] >= 0 && first_cos[v] >= 0) { partner[first_sin[v]] = first_cos[v]; partner[first_cos[v]] = first_sin[v]; }
+    }
     int hw = static_cast<int>(std::thread::hardware_concurrency());
     if (const char* e = getenv("CCU_SCHED_THREADS")) hw = atoi(e);
     threads_free = std::max(0, std::min(hw, 16) - 1);
@@ -200,6 +215,19 @@ struct Bisector {
     auto X = [](int i) { return 2 + i; };
     for (int j = 0; j < npin; ++j) net.add(S, X(loc[order[j]]), kInf);
     for (int j = m - npin; j < m; ++j) net.add(X(loc[order[j]]), T, kInf);
+    {  // tied pairs stay on one side of the cut (unless the pins already separate them)
+      std::vector<char> pin(m, 0);
+      for (int j = 0; j < npin; ++j) pin[loc[order[j]]] = 1;
+      for (int j = m - npin; j < m; ++j) pin[loc[order[j]]] |= 2;
+      for (int i = 0; i < m; ++i) {
+        const int p = partner[piece[i]];
+        if (p < 0 || loc[p] < 0 || loc[p] < i) continue;
+        const int pi = loc[p];
+        if (((pin[i] | pin[pi]) & 3) == 3) continue;
+        net.add(X(i), X(pi), kInf);
+        net.add(X(pi), X(i), kInf);
+      }
+    }
     W.ext_touched.clear();
     for (int i = 0; i < m; ++i) {
       const int v = piece[i];
@@ -388,9 +416,11 @@ bool schedule_tape(const std::vector<Node>& nodes, const ScheduleOptions& opt, S
   // times: interpreter order, specialised kernels, re-plans with other segment lengths)
   ScheduleOptions o = opt;
   o.min_piece = std::min(opt.min_piece, std::max(2, per / 2));  // (tiny segments are only asked for by tests)
+  if (const char* e = getenv("CCU_SCHED_TIE")) o.tie_sincos = atoi(e);
   uint64_t key = 1469598103934665603ull;
   auto mix = [&](uint64_t v) { key ^= v; key *= 1099511628211ull; };
   mix(static_cast<uint64_t>(n)); mix(static_cast<uint64_t>(o.min_piece)); mix(static_cast<uint64_t>(opt.pin_frac * 1e6));
+  mix(static_cast<uint64_t>(o.tie_sincos));
   for (const Node& nd : nodes) {
     uint64_t cb;
     std::memcpy(&cb, &nd.c, 8);

@@ -33,6 +33,7 @@ struct ScheduleOptions {
   int min_piece = 48;     // pieces of at most this many nodes are not split further
   int max_nodes = 600000; // longer tapes are not re-ordered (method 0)
   double pin_frac = 0.1;  // fraction of a piece pinned to either side of a cut
+  int tie_sincos = 1;     // sin(x) and cos(x) of one operand are kept in the same piece (one fused sincos in the kernel)
 };
 
 struct Schedule {

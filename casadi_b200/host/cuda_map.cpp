@@ -33,7 +33,8 @@ namespace casadi {
       void (*multi_destroy)(void*) = nullptr;
       int (*multi_size)(const void*) = nullptr;
       void* (*multi_tape)(void*, int) = nullptr;
-      int (*multi_eval_host)(void*, ccu_int, const double* const*, double* const*, const int*, const int*) = nullptr;
+      int (*multi_eval_host)(void*, ccu_int, const double* const*, double* const*, const int*, const int*,
+                             const int*, const int*) = nullptr;
       int (*last_eval_stats)(const void*, double*) = nullptr;
       // tape builder (MX functions that cannot be expanded are lowered to one scalar tape)
       void* (*builder_create)() = nullptr;
@@ -73,7 +74,7 @@ namespace casadi {
         lib.multi_destroy = reinterpret_cast<decltype(lib.multi_destroy)>(sym("ccu_multi_destroy"));
         lib.multi_size = reinterpret_cast<decltype(lib.multi_size)>(sym("ccu_multi_size"));
         lib.multi_tape = reinterpret_cast<decltype(lib.multi_tape)>(sym("ccu_multi_tape"));
-        lib.multi_eval_host = reinterpret_cast<decltype(lib.multi_eval_host)>(sym("ccu_multi_eval_host"));
+        lib.multi_eval_host = reinterpret_cast<decltype(lib.multi_eval_host)>(sym("ccu_multi_eval_host_grouped"));
         lib.last_eval_stats = reinterpret_cast<decltype(lib.last_eval_stats)>(sym("ccu_tape_last_eval_stats"));
         lib.builder_create = reinterpret_cast<decltype(lib.builder_create)>(sym("ccu_builder_create"));
         lib.builder_destroy = reinterpret_cast<decltype(lib.builder_destroy)>(sym("ccu_builder_destroy"));
@@ -321,9 +322,54 @@ namespace casadi {
   }
 
   CudaMap::CudaMap(DeserializingStream& s) : Map(s), rep_(1), flatten_(true), device_(0), builder_(nullptr), has_flag_(false) {
+    s.unpack("CudaMap::in_groups", in_groups_);
+    s.unpack("CudaMap::out_groups", out_groups_);
+    s.unpack("CudaMap::flatten", flatten_);
     // The device program is not serialized (Map::serialize_body packs f_ and n_ only, map.cpp:94-98):
     // it is re-exported from f_, exactly like a freshly created map
     export_function();
+  }
+
+  void CudaMap::serialize_body(SerializingStream &s) const {
+    Map::serialize_body(s);
+    s.pack("CudaMap::in_groups", in_groups_);
+    s.pack("CudaMap::out_groups", out_groups_);
+    s.pack("CudaMap::flatten", flatten_);
+  }
+
+  // df.map(n, "cuda") with piece-major derivative blocks; `first` = index of the first seed input of df
+  static Function grouped_derivative_map(const Function& df, casadi_int n, casadi_int ndir, casadi_int first_seed,
+                                         casadi_int n_seed, casadi_int n_sens, const std::string& name,
+                                         const std::vector<std::string>& inames, const std::vector<std::string>& onames,
+                                         const Dict& opts) {
+    CudaMap* cm = new CudaMap("cudamap" + str(n) + "_" + df.name(), df, n);
+    std::vector<casadi_int> gi(df.n_in(), 1), go(df.n_out(), 1);
+    for (casadi_int i = 0; i < n_seed; ++i) gi.at(first_seed + i) = ndir;
+    for (casadi_int i = 0; i < n_sens; ++i) go.at(i) = ndir;
+    cm->set_groups(gi, go);
+    Function dm = Function::create(cm, Dict());
+    std::vector<MX> arg = dm.mx_in();
+    std::vector<MX> res = dm(arg);
+    Dict options = opts;
+    options["allow_duplicate_io_names"] = true;
+    return Function(name, arg, res, inames, onames, options);
+  }
+
+  Function CudaMap::get_forward(casadi_int nfwd, const std::string& name, const std::vector<std::string>& inames,
+                                const std::vector<std::string>& onames, const Dict& opts) const {
+    // one direction needs no permutation; nested (flattened) and already grouped maps take the reference's route
+    if (nfwd <= 1 || rep_ != 1 || !in_groups_.empty() || !out_groups_.empty())
+      return Map::get_forward(nfwd, name, inames, onames, opts);
+    // df(arg..., res..., fseed...) -> fsens...   (function_internal.cpp: forward(nfwd) signature)
+    return grouped_derivative_map(f_.forward(nfwd), n_, nfwd, n_in_ + n_out_, n_in_, n_out_, name, inames, onames, opts);
+  }
+
+  Function CudaMap::get_reverse(casadi_int nadj, const std::string& name, const std::vector<std::string>& inames,
+                                const std::vector<std::string>& onames, const Dict& opts) const {
+    if (nadj <= 1 || rep_ != 1 || !in_groups_.empty() || !out_groups_.empty())
+      return Map::get_reverse(nadj, name, inames, onames, opts);
+    // df(arg..., res..., aseed...) -> asens...
+    return grouped_derivative_map(f_.reverse(nadj), n_, nadj, n_in_ + n_out_, n_out_, n_in_, name, inames, onames, opts);
   }
 
   CudaMap::~CudaMap() {
@@ -535,6 +581,9 @@ namespace casadi {
     int flag;
     double n_failed = 0;
     const bool reduced = !reduce_in.empty() || !reduce_out.empty();
+    std::vector<int> gi(in_groups_.begin(), in_groups_.end()), go(out_groups_.begin(), out_groups_.end());
+    const int* gip = gi.empty() ? nullptr : get_ptr(gi);
+    const int* gop = go.empty() ? nullptr : get_ptr(go);
     // reductions are defined over whole instances of f_ (CudaMapSum builds its map with keep_nested())
     casadi_assert(!reduced || rep_ == 1, "Map 'cuda': reductions over a flattened nested map");
     if (has_flag_ || reduced) {
@@ -546,11 +595,12 @@ namespace casadi {
       if (has_flag_) {
         r.push_back(&n_failed);
         red_out.push_back(1);
+        if (gop) { go.push_back(1); gop = get_ptr(go); }
       }
       flag = lib.multi_eval_host(m->tape, n_*rep_, arg, get_ptr(r), reduce_in.empty() ? nullptr : get_ptr(red_in),
-                                 get_ptr(red_out));
+                                 get_ptr(red_out), gip, gop);
     } else {
-      flag = lib.multi_eval_host(m->tape, n_*rep_, arg, res, nullptr, nullptr);
+      flag = lib.multi_eval_host(m->tape, n_*rep_, arg, res, nullptr, nullptr, gip, gop);
     }
     m->fstats.at("cuda").toc();
     {

@@ -54,6 +54,22 @@ namespace casadi {
     int eval_reduce(const double** arg, double** res, const std::vector<bool>& reduce_in,
                     const std::vector<bool>& reduce_out, void* mem) const;
 
+    /** Derivatives of the map: df.map(n, "cuda") whose seed / sensitivity blocks are read and written in the
+        direction-major layout of a derivative function directly (ccu_multi_eval_host_grouped), instead of the
+        reference's GetNonzeros column permutations on the host around the mapped call (map.cpp:219-325) */
+    Function get_forward(casadi_int nfwd, const std::string& name, const std::vector<std::string>& inames,
+                         const std::vector<std::string>& onames, const Dict& opts) const override;
+    Function get_reverse(casadi_int nadj, const std::string& name, const std::vector<std::string>& inames,
+                         const std::vector<std::string>& onames, const Dict& opts) const override;
+
+    /** Piece-major caller layout: input / output j of an instance is groups[j] pieces, piece d of instance k at
+        (d*n + k) * nnz/groups[j] (how a derivative function lays out its nfwd / nadj blocks).  Call before init. */
+    void set_groups(const std::vector<casadi_int>& in_groups, const std::vector<casadi_int>& out_groups) {
+      in_groups_ = in_groups; out_groups_ = out_groups;
+    }
+
+    void serialize_body(SerializingStream &s) const override;
+
     /// No C code generation for the device path
     bool has_codegen() const override { return false;}
 
@@ -88,6 +104,7 @@ namespace casadi {
     bool flatten_;
     Tape tape_;
     int device_;
+    std::vector<casadi_int> in_groups_, out_groups_;  // piece-major layout of derivative blocks (empty = none)
     std::vector<int> devices_;  // CASADI_CUDA_DEVICES: the devices this map is sharded over (default: device_ alone)
     // MX functions that cannot be expanded (e.g. Linsol calls) are lowered node by node through the tape
     // builder of libcasadi_cuda.so; the recorded program lives in builder_ (one compiled tape per memory)

@@ -104,6 +104,8 @@ typedef struct ccu_tape_info {
   ccu_int jit_schedule;   /* 0 = reference order, 1 = min-cut bisection order (csrc/tape_schedule.hpp)       */
   ccu_int jit_schedule_ms;/* time spent ordering and cutting the tape                                        */
   ccu_int jit_chained;    /* 1 = the segments are linked into ONE persistent kernel (one launch per evaluation)*/
+  ccu_int cse_removed;    /* arithmetic instructions the device does NOT execute: they repeat an earlier instruction on the same
+                             operand values (value numbering at tape creation; `flops` stays the reference's count)   */
 } ccu_tape_info;
 CCU_EXPORT int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info);
 
@@ -302,6 +304,14 @@ CCU_EXPORT ccu_tape* ccu_multi_tape(ccu_multi* m, int k); /* replica k (owned by
  * above.  reduce_in / reduce_out may be NULL (plain map).  Same arguments and error behaviour as the single-device call. */
 CCU_EXPORT int ccu_multi_eval_host(ccu_multi* m, ccu_int N, const double* const* arg, double* const* res,
                                    const int* reduce_in, const int* reduce_out);
+/* The same with PIECE-major caller buffers: in_groups[j] = G > 1 says that instance k of input j is G pieces of
+ * nnz_in(j)/G doubles and piece d lies at arg[j] + (d*N + k)*nnz_in(j)/G (out_groups likewise).  This is the layout
+ * of the nfwd / nadj seed and sensitivity blocks of a derivative map; the reference converts it to the instance-major
+ * layout of df.map(n) with GetNonzeros column permutations around the call (Map::get_forward / get_reverse,
+ * map.cpp:231-264, 285-318) -- here the permutation is folded into the chunk copies.  NULL = ungrouped. */
+CCU_EXPORT int ccu_multi_eval_host_grouped(ccu_multi* m, ccu_int N, const double* const* arg, double* const* res,
+                                           const int* reduce_in, const int* reduce_out, const int* in_groups,
+                                           const int* out_groups);
 
 /* ------------------------------------------------------------------------------------------------
  * Device memory helpers (so a C or C++ host needs no CUDA headers)

@@ -175,6 +175,18 @@ static void gpu_checks() {
       bool has_cuda = false;
       for (auto& nm : dF.get_function()) has_cuda = has_cuda || dF.get_function(nm).class_name() == "CudaMap";
       CHECK(has_cuda, std::string(rev ? "reverse" : "forward") + " of a cuda map must call a CudaMap");
+      // ... and nothing else: the direction-major <-> instance-major permutations (map.cpp:231-264, 285-318) are folded
+      // into the device map's chunk copies, so the derivative function is Input -> Call -> Output only
+      casadi_int n_perm = 0;
+      for (casadi_int k = 0; k < dF.n_instructions(); ++k) {
+        casadi_int o = dF.instruction_id(k);
+        n_perm += (o != OP_INPUT && o != OP_OUTPUT && o != OP_CALL);
+      }
+      CHECK(n_perm == 0, std::string(rev ? "reverse" : "forward") + "(2) of a cuda map still has " + str(n_perm) + " glue nodes");
+      Function dG = Function::deserialize(dF.serialize());
+      auto in0 = random_inputs(dref, 19 + rev, 0.1, 1.0);
+      double rel0;
+      CHECK(compare(eval(dG, in0), eval(dF, in0), &rel0) == 0, "deserialized derivative map differs");
       auto in = random_inputs(dref, 9 + rev, 0.1, 1.0);
       auto want = eval(dref, in), got = eval(dF, in);
       double rel;

@@ -30,10 +30,11 @@ def test_bisection_cuts_fewer_values_than_the_reference_order(name, seg):
 
 
 def test_quadrotor_integrator_cuts_are_the_state_vector():
-    # 20 RK4 steps of a 12-state model: every cut of the bisection order carries the 12 states (reference order: 919
-    # loads and 741 stores over 9 segments because values of all 20 steps stay alive)
+    # 20 RK4 steps of a 12-state model: every cut of the bisection order carries the 12 states plus the handful of
+    # step-invariant values that value numbering shares between the steps (thrust / mass, the three torques ...)
+    # (reference order: 919 loads and 741 stores over 9 segments because values of all 20 steps stay alive)
     s = stats("quad", 4000, 1)
-    assert s["segments"] == 2 and s["cross_loads"] == 12 and s["cross_stores"] == 12 and s["scratch_slots"] == 12
+    assert s["segments"] == 2 and 12 <= s["cross_loads"] <= 18 and s["cross_stores"] == s["cross_loads"] and s["scratch_slots"] <= 18
     assert stats("quad", 8000, 1)["segments"] == 1
 
 
