@@ -245,6 +245,26 @@ int main(int argc, char** argv) {
       return cs[i % nc];
     }, "opcover_special");
   }
+  // OP_LIFT (calculus.hpp:1006-1010; f = x, the second operand is the initial guess of a lifted variable) and
+  // OP_ASSIGN (calculus.hpp:600-606; f = x): neither is produced by expand() (MX lift expands to its first operand,
+  // mx_function.cpp:1446), so the nodes are made with the public SX::binary / SX::unary constructors
+  {
+    SX a = SX::sym("a"), b = SX::sym("b");
+    SX l1 = SX::binary(OP_LIFT, a * b + sin(a), b);
+    SX l2 = SX::binary(OP_LIFT, b, a);
+    SX as = SX::unary(OP_ASSIGN, a - b);
+    Function fl("liftfun", {a, b}, {l1 * 3 + l2, SX::binary(OP_LIFT, as, a * b), SX::unary(OP_ASSIGN, l2) * as},
+                {"a", "b"}, {"y", "z", "q"});
+    dump_tape(fl, "liftfun");
+    Rng r(11);
+    dump_case(fl, "liftfun", 64, [&](int, long long k, long long) {
+      if (k % 16 == 3) return 0.0;
+      if (k % 16 == 7) return -0.0;
+      if (k == 20) return std::numeric_limits<double>::infinity();
+      if (k == 40) return std::numeric_limits<double>::quiet_NaN();
+      return r.u(-2, 2);
+    });
+  }
   // config 4: KKT systems -- MX function [x = solve(K,b,solver); r = K*x-b] mapped serially, plus the symbolic
   // factorisation data the Linsol plugins compute in init (linsol_ldl.cpp:67-100, linsol_qr.cpp:67-84)
   {
