@@ -33,6 +33,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+T_START = time.time()
+
+
+def log(msg):
+    """progress on stderr (stdout carries the ONE JSON line)"""
+    sys.stderr.write("[bench %6.1fs] %s\n" % (time.time() - T_START, msg))
+    sys.stderr.flush()
+
+
 CONFIGS = {
     # name: tapes (golden fixtures), instances per GPU, ref_bench / cuda_bench workload, BASELINE.json config index
     "cartpole": dict(tapes=["cartpole"], N=1_000_000, ref="cartpole", idx=0, exact=False,
@@ -63,6 +72,10 @@ def parse():
     ap.add_argument("--no-interp", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="headline only: do not measure the other configs")
     ap.add_argument("--cpu-n", type=int, default=100_000, help="instances of the CPU baseline sample (>= 1e5, SURVEY 8d)")
+    ap.add_argument("--budget-s", type=float, default=420.0,
+                    help="wall-clock budget of the whole run: secondary configs / legs that would start after it are skipped (and say so)")
+    ap.add_argument("--e2e-gb", type=float, default=6.0,
+                    help="host bytes (in + out, GB) the end-to-end leg of a SECONDARY config may allocate: its batch is capped accordingly")
     return ap.parse_args()
 
 
@@ -89,7 +102,7 @@ def host_cores():
 def run_ref_bench(workload, n, mode, reps, warm, threads):
     env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="false")
     out = subprocess.run([ref_bench_exe(), workload, str(n), mode, str(threads), str(reps), str(warm)], env=env,
-                         capture_output=True, text=True, timeout=1500)
+                         capture_output=True, text=True, timeout=600)
     if out.returncode != 0:
         raise RuntimeError("ref_bench rc=%d: %s" % (out.returncode, (out.stderr or out.stdout)[-300:]))
     return json.loads(out.stdout.strip().splitlines()[-1])
@@ -449,6 +462,19 @@ def cuda_bench_exe():
     return exe if os.path.exists(exe) else None
 
 
+def e2e_cap(name, gb):
+    """largest batch of a secondary config whose caller-side buffers (inputs + outputs) stay within `gb` GB of host memory"""
+    from casadi_b200.tapeio import load_tape
+    per = 0
+    for tn in CONFIGS[name]["tapes"]:
+        if tn == "kkt_ldl":
+            per += 8 * (368 + 60 + 60 + 60)
+            continue
+        t = load_tape(tn)
+        per += 8 * (int(sum(t["nnz_in"])) + (0 if CONFIGS[name].get("reduce_out") else int(sum(t["nnz_out"]))))
+    return max(1024, int(gb * 1e9 / max(per, 1)) // 1024 * 1024)
+
+
 def measure_e2e(name, N, ctx, reps=2):
     """End to end through the plugin: the C++ CudaMap inside the relinked reference library, ordinary pageable buffers
     (tools/cuda_bench.cpp); every rank runs its own process on its own device."""
@@ -465,7 +491,11 @@ def measure_e2e(name, N, ctx, reps=2):
     torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
-    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=3000)
+    log("e2e %s: %s" % (name, " ".join(cmd[1:])))
+    try:
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    except subprocess.TimeoutExpired as e:
+        out = subprocess.CompletedProcess(cmd, 124, "", "cuda_bench timed out after 600 s: %s" % ((e.stderr or b"")[-200:],))
     ok = out.returncode == 0
     r = json.loads(out.stdout.strip().splitlines()[-1]) if ok else None
     dt = r["secs_total"] if ok else float("inf")
@@ -513,13 +543,29 @@ def main_cuda(args):
     ctx = dict(rank=rank, world=world, local=local, dev=dev, dist=dist, p64=rate.value / 1e12, hbm_peak=hbm_peak, hbm_src=hbm_src)
 
     name = args.config
+    log("headline %s: device-resident legs" % name)
     head = measure_config(name, args, ctx, K, W, headline=True)
+    log("headline value %.4g evals/s, roofline.frac %.3f" % (head["value"], head["roofline"]["frac"]))
     e2e = None if args.no_e2e else measure_e2e(name, head["N"], ctx)
+    cpu = None
+    if not args.no_cpu and world == 1 and rank == 0:
+        log("headline CPU baseline (reference openmp + serial)")
+        try:
+            cb = cpu_sample(name, args.cpu_n, 2, 1)
+            cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "serial") if k in cb}
+        except Exception as e:  # the baseline is a reported number; never lose the GPU line over it
+            cpu = {"value": None, "unit": "evals/s", "cores": host_cores(), "kind": "reference", "sample": "failed: %s" % e}
     extras = []
     if not args.no_extra:
         others = [c for c in ("cartpole", "hess_lag", "mc", "kkt", "quad_ms") if c != name] if world == 1 else (["mc"] if name != "mc" else [])
         for c in others:
+            over = world == 1 and time.time() - T_START > args.budget_s  # (every rank must take the same decision under torchrun)
+            if over:
+                extras.append({"config": config_dict(c, CONFIGS[c]["N"]), "value": None,
+                               "skipped": "time budget of %.0f s (--budget-s) reached" % args.budget_s})
+                continue
             try:
+                log("config %s: device-resident legs" % c)
                 r = measure_config(c, args, ctx, 3, 3, headline=False)
                 entry = {"config": config_dict(c, r["N"]), "value": r["value"], "unit": "evals/s", "ms_per_step": r["ms_per_step"],
                          "steps": 3, "roofline": r["roofline"], "gpu_launches": r["launches"], "parity_rel_err": r["perr"],
@@ -528,9 +574,10 @@ def main_cuda(args):
                     entry["collective"] = r["collective"]
                 if r.get("sums_hex"):
                     entry["sums_hex"] = r["sums_hex"]
-                if not args.no_e2e and world == 1:
-                    entry["e2e"] = measure_e2e(c, r["N"], ctx)
-                if not args.no_cpu and world == 1 and rank == 0:
+                if not args.no_e2e and world == 1 and time.time() - T_START <= args.budget_s:
+                    entry["e2e"] = measure_e2e(c, min(r["N"], e2e_cap(c, args.e2e_gb)), ctx)
+                if not args.no_cpu and world == 1 and rank == 0 and time.time() - T_START <= args.budget_s:
+                    log("config %s: CPU baseline" % c)
                     cb = cpu_sample(c, args.cpu_n, 2, 1)
                     entry["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "serial") if k in cb}
                 extras.append(entry)
@@ -542,13 +589,6 @@ def main_cuda(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    cpu = None
-    if not args.no_cpu and world == 1:
-        try:
-            cb = cpu_sample(name, args.cpu_n, 2, 1)
-            cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "serial") if k in cb}
-        except Exception as e:  # the baseline is a reported number; never lose the GPU line over it
-            cpu = {"value": None, "unit": "evals/s", "cores": host_cores(), "kind": "reference", "sample": "failed: %s" % e}
     cfgd = config_dict(name, head["N"])
     line = {"metric": "sx_function_evals_per_sec", "value": head["value"], "unit": "evals/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True,

@@ -345,6 +345,7 @@ void jit_options_from_env(ccu::JitOptions* o) {
   if (const char* p = getenv("CCU_JIT_RING")) o->ring = atoi(p);
   if (const char* p = getenv("CCU_JIT_CHAIN")) o->chain = atoi(p);
   if (const char* p = getenv("CCU_JIT_INTERLEAVE")) o->interleave = atoi(p);
+  if (const char* p = getenv("CCU_JIT_REMAT")) o->remat = atoi(p);
   if (const char* p = getenv("CCU_JIT_SINCOS")) o->sincos = atoi(p);
   if (const char* p = getenv("CCU_JIT_FASTOPS")) o->fastops = atoi(p);
   if (const char* p = getenv("CCU_JIT_RING_INPUTS")) o->ring_inputs = atoi(p);
@@ -537,6 +538,7 @@ int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info) {
   if (t->jit_built) {
     info->jit_segments = t->jit.segments;
     info->jit_chained = t->jit.chain ? 1 : 0;
+    info->jit_remat_cloned = t->jit.remat_cloned;
     info->jit_scratch_slots = t->jit.scratch_slots;
     info->jit_tile = t->jit.tile;
     info->jit_compile_ms = static_cast<ccu_int>(t->jit.compile_ms);
@@ -591,6 +593,30 @@ int ccu_tape_jit_plan_stats(const ccu_tape* t, int seg_instr, int schedule, ccu_
   if (!ccu::jit_plan_stats(t->source(), o, &ps, &err)) return fail("%s", err.c_str());
   stats[0] = ps.segments; stats[1] = ps.scratch_slots; stats[2] = ps.cross_loads; stats[3] = ps.cross_stores;
   stats[4] = ps.max_segment; stats[5] = static_cast<ccu_int>(ps.schedule_ms); stats[6] = ps.max_live; stats[7] = static_cast<ccu_int>(ps.mean_live);
+  return 0;
+}
+
+int ccu_tape_jit_remat_stats(const ccu_tape* t, int seg_instr, int remat, ccu_int stats[6]) {
+  if (!t || !stats) return fail("null argument");
+  ccu::JitOptions o = t->jit_opt;
+  if (seg_instr > 0) o.seg_instr = seg_instr;
+  if (remat >= 0) o.remat = remat;
+  const ccu::TapeSource tsrc = t->source();
+  o = ccu::jit_resolve(o, t->flops, &tsrc);
+  ccu::JitPlanStats ps;
+  std::string err;
+  if (!ccu::jit_plan_stats(t->source(), o, &ps, &err)) return fail("%s", err.c_str());
+  stats[0] = ps.remat_cloned; stats[1] = ps.remat_dropped; stats[2] = ps.cross_loads; stats[3] = ps.cross_stores;
+  stats[4] = ps.segments; stats[5] = ps.scratch_slots;
+  return 0;
+}
+
+int ccu_tape_set_jit_remat(ccu_tape* t, int remat) {
+  if (!t) return fail("null tape");
+  const int old = t->jit_opt.remat;
+  t->jit_opt.remat = remat;
+  if (build_jit(t)) { t->jit_opt.remat = old; return 1; }
+  t->mode = CCU_MODE_JIT;
   return 0;
 }
 

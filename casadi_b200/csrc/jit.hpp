@@ -35,6 +35,8 @@ struct JitOptions {
                           // leave their range re-evaluates the segment with the plain operators (bit-identical either way)
   std::vector<std::pair<double, double>> div_recip;  // (constant divisor, its refined reciprocal as computed on the
                                                      // device): filled by jit_build, empty = divide in the general form
+  int remat = -1;         // rematerialisation: FP64 issue slots one cross-segment value is worth (tape_schedule.hpp RematOptions);
+                          // 0 = off, -1 = automatic
   int interleave = 0;     // > 0: inside a segment, re-order windows of this many instructions level by level (ILP)
   int schedule = 1;       // 0 = reference order, fixed-length segments; 1 = min-cut bisection (tape_schedule.hpp)
   int threads = 0;        // CTA size; 0 = automatic
@@ -78,6 +80,7 @@ struct JitProgram {
   long long cross_loads = 0;    // scratch reads per evaluation
   long long cross_stores = 0;   // scratch writes per evaluation
   long long smem_moves = 0;     // shared-memory spill stores + reloads per evaluation
+  long long remat_cloned = 0;   // instructions recomputed in a reading segment instead of being stored + loaded
   int max_regs = 0;             // max registers per thread over the segments
   int cache_hits = 0;
   double compile_ms = 0;
@@ -106,6 +109,7 @@ struct JitPlanStats {
   long long max_live = 0;  // peak number of values alive inside one segment, maximum over the segments
   double mean_live = 0;    // the same, mean over the segments
   double schedule_ms = 0;
+  long long remat_cloned = 0, remat_dropped = 0;
 };
 bool jit_plan_stats(const TapeSource& src, const JitOptions& opt, JitPlanStats* out, std::string* err);
 

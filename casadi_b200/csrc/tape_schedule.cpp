@@ -546,4 +546,186 @@ void cross_traffic(const std::vector<Node>& nodes, const std::vector<int>& seg_b
   for (char c : st) *stores += c;
 }
 
+// ------------------------------------------------------------------------------------------ rematerialisation
+namespace {
+// FP64 issue slots of one recomputed instruction (branch-free division 9, sincos ~22 per pair, libm calls long)
+int remat_cost(const Node& nd) {
+  switch (nd.dop) {
+    case D_COPY: return 0;
+    case D_DIV: case D_INV: case D_SQRT: return 10;
+    case D_SIN: case D_COS: return 14;
+    case D_ADD: case D_SUB: case D_MUL: case D_NEG: case D_SQ: case D_TWICE: case D_FABS: case D_LT: case D_LE: case D_EQ:
+    case D_NE: case D_NOT: case D_AND: case D_OR: case D_IF_ELSE_ZERO: case D_FMIN: case D_FMAX: case D_SIGN: case D_COPYSIGN:
+      return 1;
+    default: return 60;
+  }
+}
+}  // namespace
+
+long long rematerialise(std::vector<Node>* nodes_io, std::vector<int>* seg_begin_io, const RematOptions& opt, RematStats* stats) {
+  const std::vector<Node>& N = *nodes_io;
+  const std::vector<int>& sb = *seg_begin_io;
+  const int n = static_cast<int>(N.size());
+  const int S = static_cast<int>(sb.size()) - 1;
+  if (S < 2 || opt.load_cost <= 0) return 0;
+  std::vector<int> seg(n, 0);
+  for (int s = 0; s < S; ++s)
+    for (int k = sb[s]; k < sb[s + 1]; ++k) seg[k] = s;
+  // consumers of every value
+  std::vector<int> cstart(n + 1, 0), cons;
+  {
+    std::vector<int> cnt(n + 1, 0);
+    auto each = [&](int k, auto&& f) {
+      const Node& nd = N[k];
+      if (nd.a >= 0) f(nd.a);
+      if (nd.b >= 0 && nd.b != nd.a) f(nd.b);
+    };
+    for (int k = 0; k < n; ++k) each(k, [&](int u) { cnt[u + 1]++; });
+    for (int k = 0; k < n; ++k) cstart[k + 1] = cstart[k] + cnt[k + 1];
+    cons.resize(cstart[n]);
+    std::vector<int> fill(cstart.begin(), cstart.end() - 1);
+    for (int k = 0; k < n; ++k) each(k, [&](int u) { cons[fill[u]++] = k; });
+  }
+  const int W = opt.load_cost, Win = std::max(1, opt.load_cost / 2);
+  std::vector<std::vector<int>> clones(S);  // original node ids recomputed inside each segment, increasing
+  std::vector<int> vert(n, -1);             // node -> flow vertex of the current network
+  std::vector<int> cand, frontier, touched;
+  FlowNet net;
+  long long total = 0;
+  for (int s = 1; s < S; ++s) {
+    const int b = sb[s], e = sb[s + 1];
+    // candidates: arithmetic ancestors (outside the segment) of its live-ins, nearest first
+    cand.clear();
+    touched.clear();
+    auto visit = [&](int u) {
+      if (u < 0 || u >= b || vert[u] != -1 || N[u].kind == K_CONST || N[u].kind == K_OUTPUT) return;
+      vert[u] = -2;
+      touched.push_back(u);
+      cand.push_back(u);
+    };
+    for (int k = b; k < e; ++k) { visit(N[k].a); visit(N[k].b); }
+    const size_t n_direct = cand.size();
+    if (n_direct == 0) continue;
+    for (size_t q = 0; q < cand.size() && static_cast<int>(cand.size()) < opt.max_candidates; ++q) {
+      const int u = cand[q];
+      if (N[u].kind != K_ARITH) continue;
+      visit(N[u].a);
+      visit(N[u].b);
+    }
+    // instruction-cache budget: the segment with its clones stays within max_segment_weight (at least half of it is
+    // always available to clones)
+    long long extra_allowed = 0;
+    if (opt.max_segment_weight > 0) {
+      long long own = 0;
+      for (int k = b; k < e; ++k) own += op_weight(N[k]);
+      extra_allowed = std::max(opt.max_segment_weight / 2, opt.max_segment_weight - own);
+    }
+    int Wcur = W, Wincur = Win;
+    std::vector<int> chosen;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+      // network: vertex 0 = source ("evaluated earlier, loaded here when needed"), 1 = sink (this segment)
+      net.reset(2);
+      for (int u : cand) vert[u] = net.add_node();
+      for (int u : cand) {
+        const bool arith = N[u].kind == K_ARITH;
+        // can this value be recomputed?  only when its operands are themselves candidates, constants or inputs we know
+        bool closed = arith;
+        if (arith) {
+          const int ops[2] = {N[u].a, N[u].b};
+          for (int v : ops)
+            if (v >= 0 && N[v].kind != K_CONST && vert[v] < 0) closed = false;
+        }
+        net.add(0, vert[u], closed ? remat_cost(N[u]) : kInf);  // on the sink side = recomputed here
+        // loaded (once) when it stays on the source side and something on the sink side reads it
+        const int z = net.add_node();
+        net.add(vert[u], z, arith ? Wcur : Wincur);
+        bool in_seg = false;
+        for (int q = cstart[u]; q < cstart[u + 1]; ++q) {
+          const int c = cons[q];
+          if (c >= b && c < e) in_seg = true;
+          else if (c < b && vert[c] >= 0) net.add(z, vert[c], kInf);
+        }
+        if (in_seg) net.add(z, 1, kInf);
+      }
+      net.maxflow(0, 1);
+      std::vector<char> reach;
+      net.reach_to(1, &reach);  // the smallest sink side
+      chosen.clear();
+      long long extra = 0;
+      for (int u : cand)
+        if (N[u].kind == K_ARITH && reach[vert[u]]) { chosen.push_back(u); extra += op_weight(N[u]); }
+      if (extra_allowed <= 0 || extra <= extra_allowed) break;
+      chosen.clear();
+      Wcur = std::max(1, Wcur / 2);
+      Wincur = std::max(1, Wincur / 2);
+    }
+    for (int u : touched) vert[u] = -1;
+    std::sort(chosen.begin(), chosen.end());
+    total += static_cast<long long>(chosen.size());
+    clones[s] = chosen;
+  }
+  if (total == 0) return 0;
+  // ---- rebuild: every segment = its clones (in tape order, hence topological) followed by its own nodes
+  std::vector<Node> out;
+  out.reserve(static_cast<size_t>(n) + total);
+  std::vector<int> newid(n, -1), cloneid(n, -1);
+  std::vector<int> nsb;
+  for (int s = 0; s < S; ++s) {
+    nsb.push_back(static_cast<int>(out.size()));
+    auto remap = [&](int v) { return v < 0 ? v : (cloneid[v] >= 0 ? cloneid[v] : newid[v]); };
+    for (int u : clones[s]) {
+      Node nd = N[u];
+      nd.a = remap(nd.a);
+      nd.b = remap(nd.b);
+      cloneid[u] = static_cast<int>(out.size());
+      out.push_back(nd);
+    }
+    for (int k = sb[s]; k < sb[s + 1]; ++k) {
+      Node nd = N[k];
+      nd.a = remap(nd.a);
+      nd.b = remap(nd.b);
+      newid[k] = static_cast<int>(out.size());
+      out.push_back(nd);
+    }
+    for (int u : clones[s]) cloneid[u] = -1;
+  }
+  nsb.push_back(static_cast<int>(out.size()));
+  // ---- values nobody reads any more (every reader recomputes them) are dropped
+  const int m = static_cast<int>(out.size());
+  std::vector<int> uses(m, 0);
+  for (int k = 0; k < m; ++k) {
+    if (out[k].a >= 0) uses[out[k].a]++;
+    if (out[k].b >= 0 && out[k].b != out[k].a) uses[out[k].b]++;
+  }
+  std::vector<char> dead(m, 0);
+  long long dropped = 0;
+  for (int k = m - 1; k >= 0; --k) {
+    if (out[k].kind != K_ARITH || uses[k] > 0) continue;
+    dead[k] = 1;
+    ++dropped;
+    if (out[k].a >= 0) uses[out[k].a]--;
+    if (out[k].b >= 0 && out[k].b != out[k].a) uses[out[k].b]--;
+  }
+  std::vector<int> fin(m, -1);
+  std::vector<Node> packed;
+  packed.reserve(m);
+  std::vector<int> psb;
+  size_t si = 0;
+  for (int k = 0; k < m; ++k) {
+    while (si < nsb.size() - 1 && nsb[si] == k) { psb.push_back(static_cast<int>(packed.size())); ++si; }
+    if (dead[k]) continue;
+    Node nd = out[k];
+    if (nd.a >= 0) nd.a = fin[nd.a];
+    if (nd.b >= 0) nd.b = fin[nd.b];
+    fin[k] = static_cast<int>(packed.size());
+    packed.push_back(nd);
+  }
+  while (psb.size() < nsb.size() - 1) psb.push_back(static_cast<int>(packed.size()));
+  psb.push_back(static_cast<int>(packed.size()));
+  if (stats) { stats->cloned = total; stats->dropped = dropped; }
+  nodes_io->swap(packed);
+  seg_begin_io->swap(psb);
+  return total;
+}
+
 }  // namespace ccu

@@ -51,4 +51,21 @@ void permute_nodes(const std::vector<Node>& in, const std::vector<int>& order, s
 // values read by a later segment than the one defining them: (distinct (value, reading segment) pairs, distinct values)
 void cross_traffic(const std::vector<Node>& nodes, const std::vector<int>& seg_begin, long long* loads, long long* stores);
 
+// Rematerialisation (recompute instead of store + load).  A value that crosses a segment boundary costs a store in the
+// segment that defines it and a load in every segment that reads it -- 16 bytes of HBM traffic per instance.  For each
+// segment a minimum cut decides which of its live-ins (and their ancestors) are RECOMPUTED inside the segment from
+// values that are loaded there anyway: a recomputed instruction costs its FP64 issue slots, a loaded value `load_cost`
+// of them, an input half that.  Reverse-mode tapes are the case it is made for: the backward sweep of an RK step reads
+// ~250 primal intermediates that are all functions of the 12 states at the start of the step (checkpoint the state,
+// recompute the step).  Recomputed instructions are the same IEEE operations on the same operand values: bit-identical.
+// Values whose every reader now recomputes them are dropped from the segment that used to define (and store) them.
+struct RematOptions {
+  int load_cost = 12;             // FP64 issue slots one cross-segment value is worth (0 = no rematerialisation)
+  int max_candidates = 40000;     // ancestors considered per segment (nearest first)
+  long long max_segment_weight = 0; // estimated SASS instructions a segment may hold with its recomputed instructions (0 = no bound)
+};
+struct RematStats { long long cloned = 0, dropped = 0; };
+// returns the number of recomputed instructions added (nodes / seg_begin are rewritten when it is > 0)
+long long rematerialise(std::vector<Node>* nodes, std::vector<int>* seg_begin, const RematOptions& opt, RematStats* stats = nullptr);
+
 }  // namespace ccu

@@ -79,6 +79,15 @@ class CudaTape:
         next (re)build of the specialised kernels."""
         capi.check(capi.lib().ccu_tape_set_jit_schedule(self.handle, schedule))
 
+    def set_jit_remat(self, remat):
+        """Rematerialisation price (FP64 issue slots per cross-segment value; 0 = off); rebuilds the kernels."""
+        capi.check(capi.lib().ccu_tape_set_jit_remat(self.handle, remat))
+
+    def jit_remat_stats(self, seg_instr=0, remat=-1):
+        st = (ctypes.c_longlong * 6)()
+        capi.check(capi.lib().ccu_tape_jit_remat_stats(self.handle, seg_instr, remat, st))
+        return dict(cloned=st[0], dropped=st[1], cross_loads=st[2], cross_stores=st[3], segments=st[4], scratch_slots=st[5])
+
     def jit_plan_stats(self, seg_instr=0, schedule=-1):
         """Plan of the specialisation (host only, nothing compiled)."""
         st = (ctypes.c_longlong * 8)()

@@ -106,6 +106,8 @@ typedef struct ccu_tape_info {
   ccu_int jit_chained;    /* 1 = the segments are linked into ONE persistent kernel (one launch per evaluation)*/
   ccu_int cse_removed;    /* arithmetic instructions the device does NOT execute: they repeat an earlier instruction on the same
                              operand values (value numbering at tape creation; `flops` stays the reference's count)   */
+  ccu_int jit_remat_cloned; /* instructions the specialised kernels RECOMPUTE in a reading segment instead of storing and loading
+                             their value (rematerialisation, csrc/tape_schedule.hpp)                                  */
 } ccu_tape_info;
 CCU_EXPORT int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info);
 
@@ -136,6 +138,13 @@ CCU_EXPORT ccu_int ccu_tape_get_jit_source(const ccu_tape* t, ccu_int segment, c
  *          largest segment (arithmetic instructions), schedule time in ms,
  *          peak values alive inside one segment (max over segments), the same (mean over segments)}. */
 CCU_EXPORT int ccu_tape_jit_plan_stats(const ccu_tape* t, int seg_instr, int schedule, ccu_int stats[8]);
+/* The same plan with rematerialisation (csrc/tape_schedule.hpp: a cross-segment value is recomputed in the reading
+ * segment when a minimum cut prices that below `remat` FP64 issue slots per stored + loaded value; 0 = off,
+ * < 0 = the tape's current setting).  stats = {recomputed instructions added, instructions dropped from their
+ * defining segment, scratch reads per evaluation, scratch writes per evaluation, segments, scratch slots}. */
+CCU_EXPORT int ccu_tape_jit_remat_stats(const ccu_tape* t, int seg_instr, int remat, ccu_int stats[6]);
+/* Sets the rematerialisation price (see above) and rebuilds the specialised kernels. */
+CCU_EXPORT int ccu_tape_set_jit_remat(ccu_tape* t, int remat);
 /* Compiles the segments of the current plan as relocatable device functions plus the persistent chain kernel and
  * links them for sm_100a (NVRTC + nvJitLink, both dlopen'ed; works without a GPU).  Returns the size of the linked
  * cubin in bytes, -1 on failure.  The reference's analogue: the "jit" option compiling the generated C of a whole

@@ -44,7 +44,7 @@ def build(verbose=True):
     base = [build_ref.CXX] + build_ref.FLAGS + build_ref.DEFINES + build_ref.FMI_INC + ["-Dcasadi_EXPORTS"] + inc
     map_o, cm_o = os.path.join(objdir, "map.o"), os.path.join(objdir, "cuda_map.o")
     ms_o, cms_o = os.path.join(objdir, "mapsum.o"), os.path.join(objdir, "cuda_mapsum.o")
-    hdrs = [os.path.join(HOST, "cuda_map.hpp"), os.path.join(HOST, "cuda_mapsum.hpp")]
+    hdrs = [os.path.join(HOST, "cuda_map.hpp"), os.path.join(HOST, "cuda_mapsum.hpp"), os.path.join(ROOT, "include", "casadi_cuda.h")]
     if newer(map_o, [patch, os.path.join(ref, "casadi/core/map.cpp")] + hdrs) or \
             newer(ms_o, [patch, os.path.join(ref, "casadi/core/mapsum.cpp")] + hdrs):
         with tempfile.TemporaryDirectory() as tmp:

@@ -101,13 +101,16 @@ def run_sources_on_host(sources, nnz_in, nnz_out, ins, N, null_in=None):
     return outs
 
 
-def run_generated(tape_name, case_name, seg_instr, nmax=40, null_in=None):
+def run_generated(tape_name, case_name, seg_instr, nmax=40, null_in=None, env=None):
     os.environ["CCU_JIT_SEG"] = str(seg_instr)
+    os.environ.update(env or {})
     try:
         t = CudaTape(load_tape(tape_name), device=-1)
         sources = t.jit_sources()
     finally:
         del os.environ["CCU_JIT_SEG"]
+        for k in (env or {}):
+            os.environ.pop(k, None)
     case = load_case(case_name)
     N = min(case["N"], nmax)
     ins = [a[:N * n] for a, n in zip(case["in"], t.nnz_in)]
@@ -125,6 +128,24 @@ def test_generated_segments_reproduce_reference_bits(tape_name, case_name, seg):
         assert nseg > 1
     for j, (g, w) in enumerate(zip(outs, want)):
         assert_bit_equal(g, w, "%s seg=%d out%d" % (case_name, seg, j))
+
+
+@pytest.mark.parametrize("tape_name,seg,remat", [("quad1_jac", 300, 24), ("quad_adj", 1200, 32), ("rocket_hess", 1200, 24),
+                                                  ("opcover", 16, 12), ("mc", 500, 24)])
+def test_rematerialised_plans_reproduce_reference_bits(tape_name, seg, remat):
+    """Rematerialisation (tape_schedule.hpp) recomputes cross-segment values inside the reading segment: the same IEEE
+    operations on the same operand values, so the outputs keep the reference's bits while the scratch traffic drops."""
+    t = CudaTape(load_tape(tape_name), device=-1)
+    base, re = t.jit_remat_stats(seg, 0), t.jit_remat_stats(seg, remat)
+    assert re["cross_loads"] + re["cross_stores"] <= base["cross_loads"] + base["cross_stores"]
+    if tape_name in ("quad_adj", "rocket_hess"):
+        # reverse sweep / block Hessian: more than half of the cross-segment values are recomputed instead
+        assert re["cloned"] > 0 and 2 * (re["cross_loads"] + re["cross_stores"]) < base["cross_loads"] + base["cross_stores"]
+    nseg, outs, want = run_generated(tape_name, tape_name, seg, nmax=200 if tape_name == "opcover" else 12,
+                                     env={"CCU_JIT_REMAT": str(remat)})
+    assert nseg > 1
+    for j, (g, w) in enumerate(zip(outs, want)):
+        assert_bit_equal(g, w, "%s seg=%d remat=%d out%d" % (tape_name, seg, remat, j))
 
 
 def test_generated_code_null_input_reads_zero():
