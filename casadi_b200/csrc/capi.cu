@@ -92,7 +92,9 @@ struct PinBuf {
 // workers (CCU_HOST_THREADS, default min(8, cores/2)) and the calling thread.
 class CopyPool {
  public:
-  static CopyPool& get() { static CopyPool pool; return pool; }
+  // never destroyed: the detached workers wait on cv_ for the life of the process, and destroying a condition variable
+  // with waiters blocks (glibc) -- a function-local static object here hung every host program at exit
+  static CopyPool& get() { static CopyPool* pool = new CopyPool; return *pool; }
   void copy(void* dst, const void* src, size_t bytes) {
     if (bytes == 0) return;
     if (workers_.empty() || bytes <= kSlice) { std::memcpy(dst, src, bytes); return; }

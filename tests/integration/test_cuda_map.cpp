@@ -176,11 +176,11 @@ static void gpu_checks() {
       for (auto& nm : dF.get_function()) has_cuda = has_cuda || dF.get_function(nm).class_name() == "CudaMap";
       CHECK(has_cuda, std::string(rev ? "reverse" : "forward") + " of a cuda map must call a CudaMap");
       // ... and nothing else: the direction-major <-> instance-major permutations (map.cpp:231-264, 285-318) are folded
-      // into the device map's chunk copies, so the derivative function is Input -> Call -> Output only
+      // into the device map's chunk copies, so the derivative function is Input (+ empty constants) -> Call -> Output only
       casadi_int n_perm = 0;
       for (casadi_int k = 0; k < dF.n_instructions(); ++k) {
         casadi_int o = dF.instruction_id(k);
-        n_perm += (o != OP_INPUT && o != OP_OUTPUT && o != OP_CALL);
+        n_perm += (o != OP_INPUT && o != OP_OUTPUT && o != OP_CALL && o != OP_CONST);  // (constants: the empty nominal outputs)
       }
       CHECK(n_perm == 0, std::string(rev ? "reverse" : "forward") + "(2) of a cuda map still has " + str(n_perm) + " glue nodes");
       Function dG = Function::deserialize(dF.serialize());

@@ -181,6 +181,7 @@ int main(int argc, char** argv) {
            "\"h2d_bytes_per_step\": %lld, \"d2h_bytes_per_step\": %lld, \"parity_rel_err\": %.3g, \"fstats\": %s}\n",
            wl.c_str(), n, memkind.c_str(), reduce ? "true" : "false", reps, secs[secs.size() / 2], secs.front(), total,
            static_cast<double>(n) * reps / total, construct, h2d, d2h, worst, stats.c_str());
+    fflush(stdout);
   } catch (std::exception& e) {
     fprintf(stderr, "cuda_bench: %s\n", e.what());
     return 1;
