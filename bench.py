@@ -256,6 +256,52 @@ def kkt_tape(device, mode=None):
     return Owned(h, [nnz, n], [n, n], device)
 
 
+UNARY_OPS = {0, 5, 6, 7, 10, 11, 12, 13, 14, 15, 16, 17, 18, 23, 26, 27, 29, 30, 33, 36, 37, 38, 39, 40, 41, 42, 86, 93, 94}
+
+
+def issue_slots(tape):
+    """FP64 issue slots the specialised kernels need per evaluation (informational, SURVEY 8d "weighted count"): the tape
+    after value numbering, one slot per +,-,*, 9 per IEEE division or sqrt (3 when the divisor is a compile-time constant:
+    its reciprocal is hoisted), 23 per sin/cos pair on one operand (14 for a lone sin or cos), 40 per other libm call --
+    the instruction counts of the branch-free sequences in csrc/ccu_ops.cuh."""
+    op, i0, i1, i2, d = (tape[k] for k in ("op", "i0", "i1", "i2", "d"))
+    last, vn, kind = {}, {}, []
+    slots = 0
+    trig = {}
+    for k in range(len(op)):
+        o = int(op[k])
+        if o == 46:
+            continue
+        if o == 44:
+            key = ("c", float(d[k]).hex())
+        elif o == 45:
+            key = ("i", int(i1[k]), int(i2[k]))
+        else:
+            a = last[int(i1[k])]
+            key = (o, a, a if o in UNARY_OPS else last[int(i2[k])])
+        v = vn.get(key)
+        if v is None:
+            v = vn[key] = len(kind)
+            kind.append(key[0])
+            if isinstance(o, int) and o not in (44, 45):
+                if o in (4, 36):
+                    slots += 3 if (o == 4 and kind[key[2]] == "c") else 9
+                elif o == 10:
+                    slots += 9
+                elif o in (13, 14):
+                    trig.setdefault(key[1], set()).add(o)
+                elif o in (0, 88):
+                    pass
+                elif o in (1, 2, 3, 5, 11, 12, 19, 20, 21, 22, 23, 24, 25, 29, 30, 31, 32, 34, 35):
+                    slots += 1
+                else:
+                    slots += 40
+        last[int(i0[k])] = v
+    for ops in trig.values():
+        slots += 23 if len(ops) == 2 else 14
+    return slots
+
+
 def golden_case(name):
     """(inputs, outputs) of the reference golden of one tape of a config; the kkt config adds the residual K*x-b, which
     the golden does not hold (exactly 0 is not expected: it is checked against the oracle's mtimes in tests/)."""
@@ -432,6 +478,16 @@ def measure_config(name, args, ctx, K, W, headline):
                 "hbm": {"achieved": ach_b, "peak": hbm_peak, "unit": "GB/s", "frac": ach_b / hbm_peak, "peak_source": hbm_src},
                 "roofline_evals_per_s": 1.0 / max(t_fp64, t_hbm),
                 "scratch": {"bytes_per_eval": scratch_bytes, "note": "cross-segment work-vector traffic of the plan (loads + stores); not algorithmic bytes"}}
+    if cfg["tapes"][dom] != "kkt_ldl":
+        try:
+            sl = issue_slots(load_tape(cfg["tapes"][dom]))
+            roofline["fp64"]["issue_slots_per_eval"] = sl
+            roofline["fp64"]["frac_of_issue_rate"] = sl * N / (dom_ms * 1e-3) / 1e12 / p64
+            roofline["fp64"]["issue_note"] = ("informational: FP64 issue slots actually needed per evaluation (IEEE division 9, by a constant 3, "
+                                               "sin/cos pair 23, after value numbering) x evals/s over the measured issue rate; the headline "
+                                               "frac counts ONE flop per tape instruction")
+        except Exception:
+            pass
     if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz"):
         # the same fraction against the FP64 rate at the clock the timed region actually ran at
         roofline["fp64"]["frac_at_sustained_clock"] = ach_f / (p64 * clocks["sm_mhz"] / clocks["sm_max_mhz"])
