@@ -89,7 +89,7 @@ struct PinBuf {
 
 // Multi-threaded memcpy between the caller's pageable buffers and the pinned staging of the host path: one thread
 // moves ~10 GB/s, the PCIe link 55 GB/s, so the copies of a chunk are cut into slices taken by a few persistent
-// workers (CCU_HOST_THREADS, default min(8, cores/2)) and the calling thread.
+// workers (CCU_HOST_THREADS, default min(16, cores - 2)) and the calling thread.
 class CopyPool {
  public:
   // never destroyed: the detached workers wait on cv_ for the life of the process, and destroying a condition variable
@@ -124,8 +124,11 @@ class CopyPool {
     std::atomic<size_t> next{0}, done{0};
   };
   CopyPool() {
-    int n = static_cast<int>(std::thread::hardware_concurrency()) / 2;
-    n = std::max(1, std::min(8, n));
+    // all but two cores of this process' share of the machine (torchrun's LOCAL_WORLD_SIZE ranks divide it), at most 16:
+    // 8 threads moved 37 GB/s on the 16-core B200 host, below the 50 GB/s of the PCIe link they feed
+    int n = static_cast<int>(std::thread::hardware_concurrency());
+    if (const char* lw = getenv("LOCAL_WORLD_SIZE")) n /= std::max(1, atoi(lw));
+    n = std::max(1, std::min(16, n - 2));
     if (const char* e = getenv("CCU_HOST_THREADS")) n = std::max(1, atoi(e));
     for (int i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
     for (auto& t : workers_) t.detach();  // workers live as long as the process

@@ -168,7 +168,8 @@ int main(int argc, char** argv) {
       Function cm = j.F;
       if (!cm.is_a("CudaMap", true))
         for (const std::string& nm : j.F.get_function()) if (j.F.get_function(nm).is_a("CudaMap", true) || j.F.get_function(nm).class_name() == "CudaMapSum") cm = j.F.get_function(nm);
-      Dict st = cm.stats();
+      Dict st;
+      try { st = cm.stats(); } catch (std::exception&) { continue; }  // (a map called from an MX wrapper used another memory object)
       for (auto&& e : st) {
         if (e.first.rfind("t_wall_", 0) != 0) continue;
         if (stats.size() > 1) stats += ", ";
