@@ -593,6 +593,7 @@ int ccu_tape_jit_plan_stats(const ccu_tape* t, int seg_instr, int schedule, ccu_
   if (schedule >= 0) o.schedule = schedule;
   const ccu::TapeSource tsrc = t->source();
   o = ccu::jit_resolve(o, t->flops, &tsrc);
+  if (t->jit_opt.remat < 0) o.remat = 0;  // the order and the cuts alone; ccu_tape_jit_remat_stats reports the plan with recomputation
   ccu::JitPlanStats ps;
   std::string err;
   if (!ccu::jit_plan_stats(t->source(), o, &ps, &err)) return fail("%s", err.c_str());

@@ -136,7 +136,8 @@ CCU_EXPORT ccu_int ccu_tape_get_jit_source(const ccu_tape* t, ccu_int segment, c
  * reference's depth-first order (sx_function.cpp:522-540); schedule 1 re-orders it (bit-identical results).
  * stats = {segments, scratch slots, scratch reads per evaluation, scratch writes per evaluation,
  *          largest segment (arithmetic instructions), schedule time in ms,
- *          peak values alive inside one segment (max over segments), the same (mean over segments)}. */
+ *          peak values alive inside one segment (max over segments), the same (mean over segments)} -- of the order and
+ * the cuts alone, without the automatic rematerialisation (ccu_tape_jit_remat_stats). */
 CCU_EXPORT int ccu_tape_jit_plan_stats(const ccu_tape* t, int seg_instr, int schedule, ccu_int stats[8]);
 /* The same plan with rematerialisation (csrc/tape_schedule.hpp: a cross-segment value is recomputed in the reading
  * segment when a minimum cut prices that below `remat` FP64 issue slots per stored + loaded value; 0 = off,
