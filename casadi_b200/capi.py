@@ -42,9 +42,11 @@ SYMBOLS = {
     "ccu_tape_jit_plan_stats": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_ll_p]),
     "ccu_tape_jit_remat_stats": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_ll_p]),
     "ccu_tape_set_jit_remat": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "ccu_tape_loop_stats": (ctypes.c_int, [c_vp, c_ll_p]),
     "ccu_tape_set_jit_schedule": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "ccu_tape_jit_link_check": (c_ll, [c_vp]),
     "ccu_tape_jit_chain_error": (ctypes.c_char_p, [c_vp]),
+    "ccu_tape_jit_compile_check": (c_ll, [c_vp, ctypes.c_char_p]),
     "ccu_map_eval_host": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp]),
     "ccu_map_eval_device": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, ctypes.c_int, c_vp]),
     "ccu_map_eval_reduce_host": (ctypes.c_int, [c_vp, c_ll, c_vp, c_vp, c_i_p, c_i_p]),
@@ -106,7 +108,8 @@ class TapeInfo(ctypes.Structure):
                                     "max_live", "grid", "ctas_per_sm", "mode", "jit_segments",
                                     "jit_scratch_slots", "jit_tile", "jit_compile_ms", "jit_cross_loads",
                                     "jit_cross_stores", "jit_max_regs", "jit_cache_hits", "jit_threads",
-                                    "jit_schedule", "jit_schedule_ms", "jit_chained", "cse_removed", "jit_remat_cloned")]
+                                    "jit_schedule", "jit_schedule_ms", "jit_chained", "cse_removed", "jit_remat_cloned", "jit_loop_iters",
+                                    "jit_loop_body", "jit_loop_slots")]
 
 
 _lib = None

@@ -23,6 +23,7 @@
 #include "comm.hpp"
 #include "interp.cuh"
 #include "jit.hpp"
+#include "tape_reroll.hpp"
 #include "layout.cuh"
 #include "reduce.cuh"
 #include "tape_builder.hpp"
@@ -351,6 +352,8 @@ void jit_options_from_env(ccu::JitOptions* o) {
   if (const char* p = getenv("CCU_JIT_CHAIN")) o->chain = atoi(p);
   if (const char* p = getenv("CCU_JIT_INTERLEAVE")) o->interleave = atoi(p);
   if (const char* p = getenv("CCU_JIT_REMAT")) o->remat = atoi(p);
+  if (const char* p = getenv("CCU_JIT_ROLL")) o->roll = atoi(p);
+  if (const char* p = getenv("CCU_JIT_ROLL_REGS")) o->roll_registers = atoi(p);
   if (const char* p = getenv("CCU_JIT_SINCOS")) o->sincos = atoi(p);
   if (const char* p = getenv("CCU_JIT_FASTOPS")) o->fastops = atoi(p);
   if (const char* p = getenv("CCU_JIT_RING_INPUTS")) o->ring_inputs = atoi(p);
@@ -544,6 +547,9 @@ int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info) {
     info->jit_segments = t->jit.segments;
     info->jit_chained = t->jit.chain ? 1 : 0;
     info->jit_remat_cloned = t->jit.remat_cloned;
+    info->jit_loop_iters = t->jit.loop_iters;
+    info->jit_loop_body = t->jit.loop_body;
+    info->jit_loop_slots = t->jit.loop_slots;
     info->jit_scratch_slots = t->jit.scratch_slots;
     info->jit_tile = t->jit.tile;
     info->jit_compile_ms = static_cast<ccu_int>(t->jit.compile_ms);
@@ -617,6 +623,27 @@ int ccu_tape_jit_remat_stats(const ccu_tape* t, int seg_instr, int remat, ccu_in
   return 0;
 }
 
+int ccu_tape_loop_stats(const ccu_tape* t, ccu_int stats[8]) {
+  if (!t || !stats) return fail("null argument");
+  for (int k = 0; k < 8; ++k) stats[k] = 0;
+  std::vector<ccu::Node> nodes;
+  long long flops = 0;
+  std::string err;
+  if (!ccu::build_graph(t->source(), &nodes, &flops, &err)) return fail("%s", err.c_str());
+  ccu::Roll roll;
+  ccu::LoopTemplate tpl;
+  if (!ccu::find_loop(nodes, &roll) || !ccu::build_loop_template(nodes, roll, &tpl, &roll.why)) {
+    g_err = "no loop: " + roll.why;
+    return 0;
+  }
+  long long before = 0;
+  for (size_t v = 0; v < nodes.size(); ++v) before += nodes[v].kind == ccu::K_ARITH && roll.where[v] == -1;
+  stats[0] = 1; stats[1] = tpl.K; stats[2] = tpl.B; stats[3] = static_cast<ccu_int>(tpl.carried.size());
+  stats[4] = static_cast<ccu_int>(tpl.ctab.size()); stats[5] = static_cast<ccu_int>(tpl.affine.size());
+  stats[6] = static_cast<ccu_int>(tpl.exit_pos.size()); stats[7] = before;
+  return 0;
+}
+
 int ccu_tape_set_jit_remat(ccu_tape* t, int remat) {
   if (!t) return fail("null tape");
   const int old = t->jit_opt.remat;
@@ -635,6 +662,16 @@ ccu_int ccu_tape_jit_link_check(const ccu_tape* t) {
   if (!ccu::jit_generate(t->source(), eff, &src, nullptr, &err)) { fail("%s", err.c_str()); return -1; }
   if (!ccu::jit_link_chain(src, eff, "sm_100a", &image, nullptr, &err)) { fail("%s", err.c_str()); return -1; }
   return static_cast<ccu_int>(image.size());
+}
+
+ccu_int ccu_tape_jit_compile_check(const ccu_tape* t, const char* dump_dir) {
+  if (!t) { fail("null tape"); return -1; }
+  const ccu::TapeSource tsrc = t->source();
+  const ccu::JitOptions eff = ccu::jit_resolve(t->jit_opt, t->flops, &tsrc);
+  std::string err;
+  const long long n = ccu::jit_compile_check(t->source(), eff, "sm_100a", dump_dir ? dump_dir : "", &err);
+  if (n < 0) fail("%s", err.c_str());
+  return n;
 }
 
 const char* ccu_tape_jit_chain_error(const ccu_tape* t) {

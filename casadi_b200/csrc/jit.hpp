@@ -37,6 +37,9 @@ struct JitOptions {
                                                      // device): filled by jit_build, empty = divide in the general form
   int remat = -1;         // rematerialisation: FP64 issue slots one cross-segment value is worth (tape_schedule.hpp RematOptions);
                           // 0 = off, -1 = automatic
+  int roll = -1;          // re-roll the time-stepping loop of the tape (tape_reroll.hpp) and run it as one persistent loop kernel:
+                          // 0 = off, 1 = whenever a loop is found, -1 = automatic
+  int roll_registers = 1; // a small loop state lives in registers (0: always in the per-CTA loop scratch)
   int interleave = 0;     // > 0: inside a segment, re-order windows of this many instructions level by level (ILP)
   int schedule = 1;       // 0 = reference order, fixed-length segments; 1 = min-cut bisection (tape_schedule.hpp)
   int threads = 0;        // CTA size; 0 = automatic
@@ -69,6 +72,12 @@ struct JitProgram {
   int segments = 0;
   std::string chain_error;             // why the plan is not chained (when it is not)
   std::vector<int> smem_bytes;  // dynamic shared memory of each kernel (staged live-ins + mbarriers)
+  // re-rolled plan (tape_reroll.hpp): kernels = [before-loop segments..., ONE persistent loop kernel, after-loop segments...]
+  int loop_kernel = -1;         // index of the loop kernel in `kernels` (-1 = flat plan)
+  int loop_iters = 0, loop_body = 0;  // iterations, arithmetic instructions per iteration
+  int loop_slots = 0;           // slots of the per-CTA loop scratch (0 = the loop state lives in registers)
+  int loop_grid = 0;            // resident CTAs of the loop kernel (filled at build from its occupancy)
+  double* d_loop = nullptr;     // loop scratch: loop_slots * threads * loop_grid doubles
   int threads = 128;
   int scratch_slots = 0;        // cross-segment values alive at once (per instance)
   long long tile = 0;           // instances per tile (0 = whole batch in one tile)
@@ -117,6 +126,11 @@ bool jit_plan_stats(const TapeSource& src, const JitOptions& opt, JitPlanStats* 
 // nvJitLink into one cubin for `arch` ("sm_100a").  Host only: works without a GPU.
 bool jit_link_chain(const std::vector<std::string>& sources, const JitOptions& opt, const std::string& arch, std::string* image,
                     int* cache_hits, std::string* err);
+
+// Compiles every kernel of the plan for `arch` with NVRTC (no GPU needed) -- a build check for CPU-only boxes; the cubins
+// are written to `dump_dir` (kernel<k>.cubin) when it is non-empty.  Returns the total size of the cubins, -1 on failure.
+long long jit_compile_check(const TapeSource& src, const JitOptions& opt, const std::string& arch, const std::string& dump_dir,
+                            std::string* err);
 
 // tile size actually used for a batch of N
 long long jit_tile_for(const JitProgram& p, long long N, int sms);

@@ -45,6 +45,9 @@ struct Node {
   int a = -1, b = -1;   // operand value ids (node indices); OUTPUT: a = source value
   int idx = 0, nz = 0;  // INPUT: input index / nonzero; OUTPUT: output index / nonzero
   double c = 0;         // CONST literal
+  // inside a re-rolled loop body (tape_reroll.hpp; both are 0 / -1 everywhere else):
+  int vary = -1;        // CONST: column of the per-iteration constant table (the literal differs between iterations)
+  int step = 0;         // INPUT: the nonzero index advances by `step` per iteration
 };
 // Validates the tape and builds the graph; `flops` = arithmetic instructions of the tape.  Instructions that
 // repeat an earlier one on the same operand values are dropped (value numbering; CCU_CSE=0 keeps them): `removed` = how

@@ -88,6 +88,16 @@ class CudaTape:
         capi.check(capi.lib().ccu_tape_jit_remat_stats(self.handle, seg_instr, remat, st))
         return dict(cloned=st[0], dropped=st[1], cross_loads=st[2], cross_stores=st[3], segments=st[4], scratch_slots=st[5])
 
+    def loop_stats(self):
+        """The time-stepping loop recovered from the unrolled tape (csrc/tape_reroll.hpp), host only."""
+        st = (ctypes.c_longlong * 8)()
+        capi.check(capi.lib().ccu_tape_loop_stats(self.handle, st))
+        d = dict(found=bool(st[0]), iters=st[1], body=st[2], carried=st[3], varying_constants=st[4], advancing_inputs=st[5],
+                 exits=st[6], before=st[7])
+        if not d["found"]:
+            d["why"] = capi.last_error()
+        return d
+
     def jit_plan_stats(self, seg_instr=0, schedule=-1):
         """Plan of the specialisation (host only, nothing compiled)."""
         st = (ctypes.c_longlong * 8)()

@@ -108,6 +108,9 @@ typedef struct ccu_tape_info {
                              operand values (value numbering at tape creation; `flops` stays the reference's count)   */
   ccu_int jit_remat_cloned; /* instructions the specialised kernels RECOMPUTE in a reading segment instead of storing and loading
                              their value (rematerialisation, csrc/tape_schedule.hpp)                                  */
+  ccu_int jit_loop_iters; /* re-rolled plan (csrc/tape_reroll.hpp): iterations of the persistent loop kernel (0 = flat plan) */
+  ccu_int jit_loop_body;  /* arithmetic instructions of one iteration                                               */
+  ccu_int jit_loop_slots; /* slots of the per-CTA loop scratch (0 = the loop state lives in registers)              */
 } ccu_tape_info;
 CCU_EXPORT int ccu_tape_get_info(const ccu_tape* t, ccu_tape_info* info);
 
@@ -144,6 +147,12 @@ CCU_EXPORT int ccu_tape_jit_plan_stats(const ccu_tape* t, int seg_instr, int sch
  * < 0 = the tape's current setting).  stats = {recomputed instructions added, instructions dropped from their
  * defining segment, scratch reads per evaluation, scratch writes per evaluation, segments, scratch slots}. */
 CCU_EXPORT int ccu_tape_jit_remat_stats(const ccu_tape* t, int seg_instr, int remat, ccu_int stats[6]);
+/* Loop re-rolling (csrc/tape_reroll.hpp): the time-stepping loop recovered from the unrolled tape (host only, no GPU).
+ * stats = {1 when a loop was found and verified, iterations, arithmetic instructions per iteration, values carried from
+ * one iteration to the next, constants that differ between iterations, input nonzeros that advance with the iteration,
+ * values of the last iteration read after the loop, arithmetic instructions before the loop}; when no loop is found
+ * stats[0] = 0 and ccu_last_error says why. */
+CCU_EXPORT int ccu_tape_loop_stats(const ccu_tape* t, ccu_int stats[8]);
 /* Sets the rematerialisation price (see above) and rebuilds the specialised kernels. */
 CCU_EXPORT int ccu_tape_set_jit_remat(ccu_tape* t, int remat);
 /* Compiles the segments of the current plan as relocatable device functions plus the persistent chain kernel and
@@ -153,6 +162,9 @@ CCU_EXPORT int ccu_tape_set_jit_remat(ccu_tape* t, int remat);
 CCU_EXPORT ccu_int ccu_tape_jit_link_check(const ccu_tape* t);
 /* Why the built specialisation runs one kernel per segment instead of the chain ("" when chained / not built). */
 CCU_EXPORT const char* ccu_tape_jit_chain_error(const ccu_tape* t);
+/* Build check for CPU-only boxes: compiles every kernel of the current plan for sm_100a with NVRTC (no GPU needed) and,
+ * when dump_dir is not NULL, writes the cubins there as kernel<k>.cubin.  Returns their total size, -1 on failure. */
+CCU_EXPORT ccu_int ccu_tape_jit_compile_check(const ccu_tape* t, const char* dump_dir);
 /* Selects the order used by subsequent (re)builds of the specialised kernels and by ccu_tape_get_jit_source. */
 CCU_EXPORT int ccu_tape_set_jit_schedule(ccu_tape* t, int schedule);
 

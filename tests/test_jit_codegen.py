@@ -60,7 +60,10 @@ extern "C" void run_seg(const ccu::IoDesc* io, long long inst0, long long n_tile
     ccu_seg(*io, inst0, n_tile, sc, flip);
   }
 }
-extern "C" long long scratch_doubles(long long n_tile) { return (long long)CCU_NSLOTS * CCU_T * ((n_tile + CCU_T - 1) / CCU_T); }  // CCU_SB divides CCU_T
+#ifndef CCU_TSLOTS  /* (a loop kernel names the slots of the tile scratch CCU_TSLOTS: its CCU_NSLOTS are the loop's own) */
+#define CCU_TSLOTS CCU_NSLOTS
+#endif
+extern "C" long long scratch_doubles(long long n_tile) { return (long long)CCU_TSLOTS * CCU_T * ((n_tile + CCU_T - 1) / CCU_T); }  // CCU_SB divides CCU_T
 """
 
 
