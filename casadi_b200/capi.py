@@ -78,6 +78,8 @@ SYMBOLS = {
     "ccu_builder_qr": (ctypes.c_int, [c_vp, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll, ctypes.c_int,
                                       ctypes.c_double, c_ll_p]),
     "ccu_builder_mtimes": (ctypes.c_int, [c_vp, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll_p]),
+    "ccu_builder_select": (c_ll, [c_vp, c_ll, c_ll, c_ll]),
+    "ccu_builder_export": (c_ll, [c_vp, c_i_p, c_i_p, c_i_p, c_i_p, c_d_p, c_ll, c_ll_p]),
     "ccu_builder_finish": (c_vp, [c_vp, c_ll, c_ll_p, c_ll, c_ll_p, ctypes.c_int]),
     "ccu_ldl_create": (c_vp, [c_ll_p, c_ll_p, c_ll_p, c_ll, ctypes.c_int]),
     "ccu_qr_create": (c_vp, [c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll_p, c_ll, ctypes.c_int, ctypes.c_double, ctypes.c_int]),
@@ -90,6 +92,7 @@ SYMBOLS = {
     "ccu_launch_count": (c_ll, []),
     "ccu_fp64_issue_rate": (ctypes.c_int, [ctypes.c_int, c_d_p]),
     "ccu_selftest_fastops": (ctypes.c_int, [ctypes.c_int, c_ll, ctypes.c_ulonglong, ctypes.POINTER(ctypes.c_ulonglong)]),
+    "ccu_selftest_host_copy": (ctypes.c_int, [c_ll, ctypes.c_int, ctypes.c_int, c_d_p]),
     "ccu_set_device": (ctypes.c_int, [ctypes.c_int]),
     "ccu_malloc": (c_vp, [c_ll]),
     "ccu_free": (ctypes.c_int, [c_vp]),
@@ -155,6 +158,13 @@ def int_array(vals):
         return None
     a = np.ascontiguousarray([1 if v else 0 for v in vals], np.int32)
     return a
+
+
+def selftest_host_copy(nbytes, dst_misalign=0, src_misalign=0):
+    """GB/s of the staging copy of the host path (raises when the copy is not exact)."""
+    r = ctypes.c_double(0)
+    check(lib().ccu_selftest_host_copy(nbytes, dst_misalign, src_misalign, ctypes.byref(r)))
+    return r.value
 
 
 def selftest_fastops(n, seed=1, device=0):

@@ -29,6 +29,8 @@
 #include "tape_builder.hpp"
 #include "tape_compile.hpp"
 
+namespace ccu { void host_copy_slice(void* dst, const void* src, size_t bytes, bool streaming); }  // hostcopy.cpp
+
 namespace {
 
 thread_local std::string g_err;
@@ -98,7 +100,7 @@ class CopyPool {
   static CopyPool& get() { static CopyPool* pool = new CopyPool; return *pool; }
   void copy(void* dst, const void* src, size_t bytes) {
     if (bytes == 0) return;
-    if (workers_.empty() || bytes <= kSlice) { std::memcpy(dst, src, bytes); return; }
+    if (workers_.empty() || bytes <= kSlice) { ccu::host_copy_slice(dst, src, bytes, streaming_ && bytes >= (256u << 10)); return; }
     auto job = std::make_shared<Job>();
     job->dst = static_cast<char*>(dst); job->src = static_cast<const char*>(src); job->bytes = bytes;
     job->slices = (bytes + kSlice - 1) / kSlice;
@@ -131,6 +133,7 @@ class CopyPool {
     if (const char* lw = getenv("LOCAL_WORLD_SIZE")) n /= std::max(1, atoi(lw));
     n = std::max(1, std::min(16, n - 2));
     if (const char* e = getenv("CCU_HOST_THREADS")) n = std::max(1, atoi(e));
+    if (const char* e = getenv("CCU_HOST_STREAMING")) streaming_ = atoi(e) != 0;  // non-temporal stores (hostcopy.cpp), on by default
     for (int i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
     for (auto& t : workers_) t.detach();  // workers live as long as the process
   }
@@ -139,7 +142,7 @@ class CopyPool {
       const size_t k = j.next.fetch_add(1);
       if (k >= j.slices) return;
       const size_t off = k * kSlice, len = std::min(kSlice, j.bytes - off);
-      std::memcpy(j.dst + off, j.src + off, len);
+      ccu::host_copy_slice(j.dst + off, j.src + off, len, streaming_);
       if (j.done.fetch_add(1) + 1 == j.slices) { std::lock_guard<std::mutex> lk(mu_); cv_done_.notify_all(); }
     }
   }
@@ -157,6 +160,7 @@ class CopyPool {
     }
   }
   std::vector<std::thread> workers_;
+  bool streaming_ = true;
   std::mutex mu_, run_mu_;
   std::condition_variable cv_, cv_done_;
   std::shared_ptr<Job> cur_;
@@ -1387,6 +1391,26 @@ int ccu_builder_mtimes(ccu_builder* b, const ccu_int* x, const ccu_int* sp_x, co
   return 0;
 }
 
+ccu_int ccu_builder_select(ccu_builder* b, ccu_int c, ccu_int x, ccu_int y) {
+  if (!b) { fail("null builder"); return -1; }
+  const ccu_int n = b->b.n_values();
+  if (c < 0 || c >= n || x < 0 || x >= n || y < 0 || y >= n) { fail("ccu_builder_select: invalid operand handle"); return -1; }
+  return b->b.select(c, x, y);
+}
+
+ccu_int ccu_builder_export(const ccu_builder* b, int* op, int* i0, int* i1, int* i2, double* d, ccu_int cap, ccu_int* sz_w) {
+  if (!b) { fail("null builder"); return -1; }
+  const ccu::TapeSource s = b->b.source({}, {});
+  const ccu_int n = std::min<ccu_int>(s.n_instr, cap > 0 ? cap : 0);
+  if (op) std::copy(s.op, s.op + n, op);
+  if (i0) std::copy(s.i0, s.i0 + n, i0);
+  if (i1) std::copy(s.i1, s.i1 + n, i1);
+  if (i2) std::copy(s.i2, s.i2 + n, i2);
+  if (d) std::copy(s.d, s.d + n, d);
+  if (sz_w) *sz_w = s.sz_w;
+  return s.n_instr;
+}
+
 ccu_tape* ccu_builder_finish(ccu_builder* b, ccu_int n_in, const ccu_int* nnz_in, ccu_int n_out, const ccu_int* nnz_out,
                              int device) {
   if (!b) { fail("null builder"); return nullptr; }
@@ -1505,5 +1529,23 @@ int ccu_memcpy_d2h(void* dst, const void* src, ccu_int bytes, void* stream) {
 }
 int ccu_stream_sync(void* stream) { CCU_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream))); return 0; }
 int ccu_device_sync(void) { CCU_CUDA(cudaDeviceSynchronize()); return 0; }
+
+
+int ccu_selftest_host_copy(long long bytes, int dst_misalign, int src_misalign, double* gb_per_s) {
+  if (bytes < 0 || dst_misalign < 0 || dst_misalign > 4096 || src_misalign < 0 || src_misalign > 4096) return fail("ccu_selftest_host_copy: invalid argument");
+  const size_t n = static_cast<size_t>(bytes), guard = 64;
+  std::vector<unsigned char> src(n + src_misalign + 1), dst(n + dst_misalign + 2 * guard, 0xA5);
+  unsigned long long x = 0x9E3779B97F4A7C15ull;
+  for (size_t i = 0; i < n; ++i) { x = x * 6364136223846793005ull + 1442695040888963407ull; src[src_misalign + i] = static_cast<unsigned char>(x >> 56); }
+  unsigned char* d = dst.data() + guard + dst_misalign;
+  const auto t0 = std::chrono::steady_clock::now();
+  CopyPool::get().copy(d, src.data() + src_misalign, n);
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (gb_per_s) *gb_per_s = sec > 0 ? static_cast<double>(n) / sec / 1e9 : 0;
+  if (n && std::memcmp(d, src.data() + src_misalign, n) != 0) return fail("ccu_selftest_host_copy: the copy differs from its source");
+  for (size_t i = 0; i < guard + dst_misalign; ++i) if (dst[i] != 0xA5) return fail("ccu_selftest_host_copy: bytes before the destination were written");
+  for (size_t i = 0; i < guard; ++i) if (d[n + i] != 0xA5) return fail("ccu_selftest_host_copy: bytes after the destination were written");
+  return 0;
+}
 
 }  // extern "C"

@@ -2,6 +2,7 @@
  * CudaMap -- see cuda_map.hpp.  New file for casadi/core/.
  */
 #include "cuda_map.hpp"
+#include "integrator_impl.hpp"
 #include "linsol.hpp"
 #include "multiplication.hpp"
 #include "mx_node.hpp"
@@ -12,6 +13,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <mutex>
 
@@ -49,6 +51,8 @@ namespace casadi {
                         const ccu_int*, ccu_int*, ccu_int, int, double, ccu_int*) = nullptr;
       int (*builder_mtimes)(void*, const ccu_int*, const ccu_int*, const ccu_int*, const ccu_int*, ccu_int*,
                             const ccu_int*) = nullptr;
+      ccu_int (*builder_select)(void*, ccu_int, ccu_int, ccu_int) = nullptr;
+      ccu_int (*builder_export)(const void*, int*, int*, int*, int*, double*, ccu_int, ccu_int*) = nullptr;
     };
 
     CudaLib& cuda_lib() {
@@ -85,6 +89,8 @@ namespace casadi {
         lib.builder_ldl = reinterpret_cast<decltype(lib.builder_ldl)>(sym("ccu_builder_ldl"));
         lib.builder_qr = reinterpret_cast<decltype(lib.builder_qr)>(sym("ccu_builder_qr"));
         lib.builder_mtimes = reinterpret_cast<decltype(lib.builder_mtimes)>(sym("ccu_builder_mtimes"));
+        lib.builder_select = reinterpret_cast<decltype(lib.builder_select)>(sym("ccu_builder_select"));
+        lib.builder_export = reinterpret_cast<decltype(lib.builder_export)>(sym("ccu_builder_export"));
         if (!ok) {
           lib.error = "'" + name + "' does not export the casadi_cuda.h entry points";
           lib.handle = nullptr;
@@ -304,11 +310,94 @@ namespace casadi {
         }
       }
 
+      // A fixed-step integrator with an explicit step function (the "rk" plugin, runge_kutta.cpp:68-135): replays
+      // Integrator::eval (integrator.cpp:354-530) for the case without events and without backward states.  With the
+      // time grid fixed, every step time t_k + j*h and step length h is a host constant computed by the reference's own
+      // expressions (FixedStepIntegrator::advance_noevent, integrator.cpp:2034-2073), and the evaluation is nt * nj
+      // calls of the discrete-time function "step" (and of its forward-mode function for an augmented integrator,
+      // FixedStepIntegrator::stepF, :2119-2150) with the quadrature accumulated as q = qf + 1.*q_prev: a straight-line
+      // program whose loop structure the tape re-rolling pass of libcasadi_cuda.so recovers.
+      // Controls: interval k uses u[k] -- the reference keeps the previous interval's control while it compares equal
+      // (Integrator::next_stop, :2566-2583), which differs only when consecutive controls are zeros of opposite sign.
+      void call_fixed_step(const Function& f, const FixedStepIntegrator* I, const std::vector<const Vals*>& arg,
+                           std::vector<Vals*>& res) {
+        const std::string who = "Map 'cuda': integrator '" + f.name() + "' (" + f.class_name() + "): ";
+        casadi_assert(I->has_function("step"), who + "implicit step functions (collocation) have no device lowering");
+        casadi_assert(I->ne_ == 0, who + "events (zero-crossing functions) have no device lowering");
+        casadi_assert(I->nrx_ == 0 && I->nadj_ == 0, who + "backward states (adjoint sensitivities) have no device "
+                      "lowering; use forward mode or map the derivative of the simplified integrator");
+        casadi_assert(I->nz_ == 0, who + "algebraic variables have no device lowering");
+        const Function& F = I->get_function("step");
+        const casadi_int nfwd = I->nfwd_;
+        Function dF;
+        if (nfwd > 0) dF = I->get_function(FunctionInternal::forward_name("step", nfwd));
+        const casadi_int nx = I->nx_, nq = I->nq_, np = I->np_, nu = I->nu_, nv = F.nnz_out(STEP_VF) * (1 + nfwd);
+        const casadi_int nx1 = I->nx1_, nq1 = I->nq1_, np1 = I->np1_, nu1 = I->nu1_, nv1 = F.nnz_out(STEP_VF);
+        const casadi_int nt = I->nt();
+        const ccu_int zero = cst(0.);
+        auto take = [&](casadi_int j, casadi_int off, casadi_int n) {  // casadi_copy with a null source clears
+          Vals r(n, zero);
+          if (arg.at(j)) for (casadi_int i = 0; i < n; ++i) r[i] = arg[j]->at(off + i);
+          return r;
+        };
+        Vals x = take(INTEGRATOR_X0, 0, nx), p = take(INTEGRATOR_P, 0, np), q(nq, zero);
+        Vals v(nv, cst(std::numeric_limits<double>::quiet_NaN()));  // FixedStepIntegrator::reset, :2230
+        double t = I->t0_;
+        for (casadi_int k = 0; k < nt; ++k) {
+          const double t_next = I->tout_.at(k);
+          Vals u = take(INTEGRATOR_U, k * nu, nu);
+          const casadi_int nj = I->disc_.at(k + 1) - I->disc_.at(k);
+          const double h = (t_next - t) / nj;
+          for (casadi_int j = 0; j < nj; ++j) {
+            const double tj = t + j * h;
+            const Vals x_prev = x, v_prev = v, q_prev = q;
+            const Vals tv(1, cst(tj)), hv(1, cst(h));
+            const Vals x0(x_prev.begin(), x_prev.begin() + nx1), v0(v_prev.begin(), v_prev.begin() + nv1),
+                       pp(p.begin(), p.begin() + np1), uu(u.begin(), u.begin() + nu1);
+            Vals xf(nx1, zero), vf(nv1, zero), qf(nq1, zero);
+            {
+              std::vector<const Vals*> a(F.n_in(), nullptr);
+              a[STEP_T] = &tv; a[STEP_H] = &hv; a[STEP_X0] = &x0; a[STEP_V0] = &v0; a[STEP_P] = &pp; a[STEP_U] = &uu;
+              std::vector<Vals*> r(F.n_out(), nullptr);
+              r[STEP_XF] = &xf; r[STEP_VF] = &vf; r[STEP_QF] = &qf;
+              call(F, a, r);
+            }
+            std::copy(xf.begin(), xf.end(), x.begin());
+            std::copy(vf.begin(), vf.end(), v.begin());
+            std::copy(qf.begin(), qf.end(), q.begin());
+            if (nfwd > 0) {
+              const Vals fx0(x_prev.begin() + nx1, x_prev.end()), fv0(v_prev.begin() + nv1, v_prev.end()),
+                         fp(p.begin() + np1, p.end()), fu(u.begin() + nu1, u.end());
+              Vals fxf(nx - nx1, zero), fvf(nv - nv1, zero), fqf(nq - nq1, zero);
+              std::vector<const Vals*> a(dF.n_in(), nullptr);
+              a[STEP_T] = &tv; a[STEP_H] = &hv; a[STEP_X0] = &x0; a[STEP_V0] = &v0; a[STEP_P] = &pp; a[STEP_U] = &uu;
+              a[STEP_NUM_IN + STEP_XF] = &xf; a[STEP_NUM_IN + STEP_VF] = &vf; a[STEP_NUM_IN + STEP_QF] = &qf;
+              a[STEP_NUM_IN + STEP_NUM_OUT + STEP_X0] = &fx0; a[STEP_NUM_IN + STEP_NUM_OUT + STEP_V0] = &fv0;
+              a[STEP_NUM_IN + STEP_NUM_OUT + STEP_P] = &fp; a[STEP_NUM_IN + STEP_NUM_OUT + STEP_U] = &fu;
+              std::vector<Vals*> r(dF.n_out(), nullptr);
+              r[STEP_XF] = &fxf; r[STEP_VF] = &fvf; r[STEP_QF] = &fqf;
+              call(dF, a, r);
+              std::copy(fxf.begin(), fxf.end(), x.begin() + nx1);
+              std::copy(fvf.begin(), fvf.end(), v.begin() + nv1);
+              std::copy(fqf.begin(), fqf.end(), q.begin() + nq1);
+            }
+            // casadi_axpy(nq_, 1., q_prev, q)
+            const ccu_int one = cst(1.);
+            for (casadi_int i = 0; i < nq; ++i) q[i] = op(OP_ADD, q[i], op(OP_MUL, one, q_prev[i]));
+          }
+          t = t_next;
+          if (res.at(INTEGRATOR_XF)) std::copy(x.begin(), x.end(), res[INTEGRATOR_XF]->begin() + k * nx);
+          if (res.at(INTEGRATOR_QF)) std::copy(q.begin(), q.end(), res[INTEGRATOR_QF]->begin() + k * nq);
+        }
+      }
+
       void call(const Function& f, const std::vector<const Vals*>& arg, std::vector<Vals*>& res) {
         if (f.is_a("SXFunction")) {
           call_sx(f, arg, res);
         } else if (f.is_a("MXFunction")) {
           call_mx(f, arg, res);
+        } else if (auto* I = dynamic_cast<const FixedStepIntegrator*>(f.get())) {
+          call_fixed_step(f, I, arg, res);
         } else {
           casadi_error("Map 'cuda': embedded function '" + f.name() + "' of class " + f.class_name()
                        + " has no device lowering");
@@ -419,6 +508,8 @@ namespace casadi {
     return t;
   }
 
+  static bool lowerable_class(const Function& f);
+
   void CudaMap::export_function() {
     builder_ = nullptr;
     has_flag_ = false;
@@ -443,8 +534,8 @@ namespace casadi {
       } catch (std::exception& e) {
         // ... anything else (e.g. a Linsol call, solve_impl.hpp:57-73: "eval_sx not defined") is lowered
         // node by node through the tape builder; unsupported nodes raise from there
-        casadi_assert(leaf_.is_a("MXFunction"), "Map 'cuda': function '" + leaf_.name() + "' (" + leaf_.class_name()
-                      + ") is neither an SX nor an MX function");
+        casadi_assert(lowerable_class(leaf_), "Map 'cuda': function '" + leaf_.name() + "' (" + leaf_.class_name()
+                      + ") is neither an SX function, an MX function nor a fixed-step integrator");
         lower_mx();
         return;
       }
@@ -454,43 +545,77 @@ namespace casadi {
     tape_ = export_tape(sx_);
   }
 
-  void CudaMap::lower_mx() {
+  // Lower `leaf` node by node through the tape builder; returns the builder (owned by the caller)
+  static void* lower_function(const Function& leaf, bool* has_flag) {
     CudaLib& lib = cuda_lib();
     casadi_assert(lib.handle!=nullptr, "Map 'cuda': " + lib.error);
-    casadi_assert(!leaf_.has_free(), "Map 'cuda': function '" + leaf_.name() + "' has free variables "
-                  + str(leaf_.get_free()) + " and cannot be evaluated");
+    casadi_assert(!leaf.has_free(), "Map 'cuda': function '" + leaf.name() + "' has free variables "
+                  + str(leaf.get_free()) + " and cannot be evaluated");
     Lowering L(lib);
+    *has_flag = false;
     try {
-      std::vector<Vals> in(leaf_.n_in()), out(leaf_.n_out());
-      std::vector<const Vals*> a(leaf_.n_in());
-      std::vector<Vals*> r(leaf_.n_out());
-      for (casadi_int j=0; j<leaf_.n_in(); ++j) {
-        in[j].resize(leaf_.nnz_in(j));
-        for (casadi_int e=0; e<leaf_.nnz_in(j); ++e) in[j][e] = lib.builder_input(L.b, j, e);
+      std::vector<Vals> in(leaf.n_in()), out(leaf.n_out());
+      std::vector<const Vals*> a(leaf.n_in());
+      std::vector<Vals*> r(leaf.n_out());
+      for (casadi_int j=0; j<leaf.n_in(); ++j) {
+        in[j].resize(leaf.nnz_in(j));
+        for (casadi_int e=0; e<leaf.nnz_in(j); ++e) in[j][e] = lib.builder_input(L.b, j, e);
         a[j] = &in[j];
       }
-      for (casadi_int j=0; j<leaf_.n_out(); ++j) {
-        out[j].assign(leaf_.nnz_out(j), L.cst(0.));
+      for (casadi_int j=0; j<leaf.n_out(); ++j) {
+        out[j].assign(leaf.nnz_out(j), L.cst(0.));
         r[j] = &out[j];
       }
-      L.call(leaf_, a, r);
-      for (casadi_int j=0; j<leaf_.n_out(); ++j)
-        for (casadi_int e=0; e<leaf_.nnz_out(j); ++e) lib.builder_output(L.b, j, e, out[j][e]);
+      L.call(leaf, a, r);
+      for (casadi_int j=0; j<leaf.n_out(); ++j)
+        for (casadi_int e=0; e<leaf.nnz_out(j); ++e) lib.builder_output(L.b, j, e, out[j][e]);
       // instances whose QR factorisation is numerically singular make the reference's map fail
       // (LinsolQr::nfact returns 1, linsol_qr.cpp:146-163): counted in one extra, summed output
       if (L.fail_count >= 0) {
-        lib.builder_output(L.b, leaf_.n_out(), 0, L.fail_count);
-        has_flag_ = true;
+        lib.builder_output(L.b, leaf.n_out(), 0, L.fail_count);
+        *has_flag = true;
       }
     } catch (...) {
       lib.builder_destroy(L.b);
       throw;
     }
-    builder_ = L.b;
+    return L.b;
+  }
+
+  static bool lowerable_class(const Function& f) {
+    return f.is_a("MXFunction") || dynamic_cast<const FixedStepIntegrator*>(f.get()) != nullptr;
+  }
+
+  void CudaMap::lower_mx() {
+    builder_ = lower_function(leaf_, &has_flag_);
     tape_ = Tape();
     for (casadi_int j=0; j<leaf_.n_in(); ++j) tape_.nnz_in.push_back(leaf_.nnz_in(j));
     for (casadi_int j=0; j<leaf_.n_out(); ++j) tape_.nnz_out.push_back(leaf_.nnz_out(j));
     if (has_flag_) tape_.nnz_out.push_back(1);
+  }
+
+  CudaMap::Tape CudaMap::lowered_tape(const Function& f) {
+    if (f.is_a("SXFunction")) return export_tape(f);
+    try {
+      return export_tape(f.expand());
+    } catch (std::exception& e) {
+      casadi_assert(lowerable_class(f), "Map 'cuda': function '" + f.name() + "' (" + f.class_name()
+                    + ") is neither an SX function, an MX function nor a fixed-step integrator");
+    }
+    CudaLib& lib = cuda_lib();
+    bool flag = false;
+    void* b = lower_function(f, &flag);
+    Tape t;
+    ccu_int sz_w = 0;
+    ccu_int n = lib.builder_export(b, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &sz_w);
+    t.op.resize(n); t.i0.resize(n); t.i1.resize(n); t.i2.resize(n); t.d.resize(n);
+    lib.builder_export(b, get_ptr(t.op), get_ptr(t.i0), get_ptr(t.i1), get_ptr(t.i2), get_ptr(t.d), n, &sz_w);
+    lib.builder_destroy(b);
+    t.sz_w = sz_w;
+    for (casadi_int j=0; j<f.n_in(); ++j) t.nnz_in.push_back(f.nnz_in(j));
+    for (casadi_int j=0; j<f.n_out(); ++j) t.nnz_out.push_back(f.nnz_out(j));
+    if (flag) t.nnz_out.push_back(1);
+    return t;
   }
 
   void CudaMap::init(const Dict& opts) {

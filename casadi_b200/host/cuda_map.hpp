@@ -86,6 +86,12 @@ namespace casadi {
     };
     static Tape export_tape(const Function& f);
 
+    /** The tape one device thread evaluates for `f`: export_tape for an SX function or an MX function that expands;
+        otherwise the function lowered node by node through the tape builder (Linsol calls, fixed-step integrators).
+        Needs libcasadi_cuda.so but no device: host-side checks evaluate it instance by instance.  A last extra output
+        of one nonzero is present when the lowering counts failed QR factorisations. */
+    static Tape lowered_tape(const Function& f);
+
     /** Keep a mapped function that is itself a Map as ONE instance (its inner map is expanded into the tape) instead
         of flattening it to n*d device instances.  CudaMapSum needs this: a reduced input belongs to a whole
         instance of f_ and a reduced output is the sum of whole f_ outputs (mapsum.cpp:154-186).  Call before init. */

@@ -244,6 +244,14 @@ CCU_EXPORT int ccu_builder_qr(ccu_builder* b, const ccu_int* sp_a, const ccu_int
 /* z += x*y (handles in z are replaced) */
 CCU_EXPORT int ccu_builder_mtimes(ccu_builder* b, const ccu_int* x, const ccu_int* sp_x, const ccu_int* y,
                                   const ccu_int* sp_y, ccu_int* z, const ccu_int* sp_z);
+/* c != 0 ? a : b with the selected operand's bits (sign of zero, NaN) preserved; recorded as seven operations of the
+ * reference's set (if_else_zero, not, copysign, add, mul) -> handle */
+CCU_EXPORT ccu_int ccu_builder_select(ccu_builder* b, ccu_int c, ccu_int x, ccu_int y);
+/* The recorded program in the reference's tape layout (the arrays ccu_tape_create takes): copies up to `cap`
+ * instructions into op / i0 / i1 / i2 / d (each may be NULL), stores the work-vector size in *sz_w (may be NULL) and
+ * returns the instruction count.  Needs no device: what a host-side check evaluates instance by instance. */
+CCU_EXPORT ccu_int ccu_builder_export(const ccu_builder* b, int* op, int* i0, int* i1, int* i2, double* d, ccu_int cap,
+                                      ccu_int* sz_w);
 /* compile what has been recorded; the builder can be destroyed afterwards */
 CCU_EXPORT ccu_tape* ccu_builder_finish(ccu_builder* b, ccu_int n_in, const ccu_int* nnz_in, ccu_int n_out,
                                         const ccu_int* nnz_out, int device);
@@ -286,6 +294,11 @@ CCU_EXPORT int ccu_fp64_issue_rate(int device, double* ops_per_s);
  * a bit although the fast path did not flag the operands (must be 0), counts[1] = flagged (re-evaluated by the plain
  * operator in a kernel), counts[2] = checks.  Restates nothing of the reference: parity infrastructure of this library. */
 CCU_EXPORT int ccu_selftest_fastops(int device, long long n, unsigned long long seed, unsigned long long counts[3]);
+/* Self test of the host path's staging copy (the multi-threaded copy with non-temporal stores between a caller's
+ * pageable buffer and the pinned staging, csrc/hostcopy.cpp): copies `bytes` bytes between two heap buffers offset by
+ * dst_misalign / src_misalign bytes and compares with the source and the guard bytes around the destination.  Needs
+ * no GPU.  Returns 0 when identical; *gb_per_s (may be NULL) receives the copy rate. */
+CCU_EXPORT int ccu_selftest_host_copy(long long bytes, int dst_misalign, int src_misalign, double* gb_per_s);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU.  Instances are independent (map.cpp:147-155): the batch is cut into contiguous shards of

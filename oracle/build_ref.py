@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Build the UNMODIFIED reference (casadi core + linsol_ldl/linsol_qr plugins) into oracle/_ref/.
+"""Build the UNMODIFIED reference (casadi core + the linsol_ldl / linsol_qr / integrator_rk / rootfinder_newton
+plugins) into oracle/_ref/.
 
 TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is on the product path; the
 product (casadi_b200/) never imports, links or executes anything built here.
@@ -25,6 +26,7 @@ host code has no FMA contraction on x86-64.
 
 Outputs (all under oracle/_ref/, git-ignored, shipped to the GPU box by gpurun):
   lib/libcasadi.so  lib/libcasadi_linsol_ldl.so  lib/libcasadi_linsol_qr.so
+  lib/libcasadi_integrator_rk.so  lib/libcasadi_rootfinder_newton.so
   obj/*.o           (kept so tests/integration can relink a patched map.o)
 """
 import concurrent.futures as cf
@@ -49,6 +51,15 @@ FMI_INC = ["-I" + os.path.join(REF, "external_packages/FMI-Standard-2.0.2/header
            "-I" + os.path.join(REF, "external_packages/FMI-Standard-3.0/headers")]
 FLAGS = ["-std=c++17", "-fopenmp", "-DWITH_OPENMP", "-pthread", "-fPIC", "-O3", "-DNDEBUG",
          "-fvisibility=hidden", "-fvisibility-inlines-hidden", "-w"]
+
+
+# plugin -> its two source files under casadi/solvers (the plugin class and its registration)
+PLUGINS = {
+    "linsol_ldl": ("linsol_ldl.cpp", "linsol_ldl_meta.cpp"),
+    "linsol_qr": ("linsol_qr.cpp", "linsol_qr_meta.cpp"),
+    "integrator_rk": ("runge_kutta.cpp", "runge_kutta_meta.cpp"),
+    "rootfinder_newton": ("newton.cpp", "newton_meta.cpp"),
+}
 
 
 def public_flags():
@@ -113,8 +124,8 @@ def generate_headers():
         "CASADI_IS_RELEASE": "0", "CASADI_VERSION": "3.7.2", "git_revision": "reference-tree",
         "git_describe": "3.7.2", "feature_list": "\\n * dynamic-loading\\n * openmp\\n * thread",
         "CMAKE_BUILD_TYPE": "Release", "CMAKE_CXX_COMPILER_ID": "GNU",
-        "CASADI_CMAKE_CXX_COMPILER": CXX, "CASADI_MODULES": "casadi;casadi_linsol_ldl;casadi_linsol_qr",
-        "CASADI_PLUGINS": "Linsol::ldl;Linsol::qr", "CASADI_INSTALL_PREFIX": os.path.join(OUT),
+        "CASADI_CMAKE_CXX_COMPILER": CXX, "CASADI_MODULES": "casadi;" + ";".join("casadi_" + p for p in PLUGINS),
+        "CASADI_PLUGINS": "Linsol::ldl;Linsol::qr;Integrator::rk;Rootfinder::newton", "CASADI_INSTALL_PREFIX": os.path.join(OUT),
         "CMAKE_SHARED_LIBRARY_PREFIX": "lib", "CMAKE_SHARED_LIBRARY_SUFFIX": ".so",
         "CMAKE_C_OUTPUT_EXTENSION": ".o", "casadi_lapack_libraries": "",
     }
@@ -124,7 +135,7 @@ def generate_headers():
     write_if_changed(os.path.join(gen, "casadi/config.h"), tpl)
     write_if_changed(os.path.join(gen, "casadi/core/casadi_export.h"),
                      EXPORT_H.format(G="CASADI_EXPORT", N="CASADI"))
-    for p in ("linsol_ldl", "linsol_qr"):
+    for p in PLUGINS:
         write_if_changed(os.path.join(gen, "casadi/solvers/casadi_%s_export.h" % p),
                          EXPORT_H.format(G="CASADI_%s_EXPORT" % p.upper(), N="CASADI_%s" % p.upper()))
     # runtime strings (what casadi/generate_runtime.cmake emits)
@@ -166,9 +177,9 @@ def build(jobs=None, verbose=True):
         core_objs.append(o)
         work.append((s, o, ["-Dcasadi_EXPORTS"]))
     plug_objs = {}
-    for p in ("linsol_ldl", "linsol_qr"):
+    for p in PLUGINS:
         plug_objs[p] = []
-        for s in (p + ".cpp", p + "_meta.cpp"):
+        for s in PLUGINS[p]:
             o = os.path.join(objdir, "plugin_" + s[:-4] + ".o")
             plug_objs[p].append(o)
             work.append((os.path.join(REF, "casadi/solvers", s), o, ["-Dcasadi_%s_EXPORTS" % p]))

@@ -65,15 +65,22 @@ def build(verbose=True):
     new_objs = [map_o, cm_o, ms_o, cms_o]
     if newer(lib, new_objs + ref_objs):
         subprocess.check_call([build_ref.CXX, "-shared", "-fopenmp", "-pthread", "-o", lib] + ref_objs + new_objs + ["-ldl"])
-    for p in ("libcasadi_linsol_ldl.so", "libcasadi_linsol_qr.so"):
+    for p in ("libcasadi_%s.so" % q for q in build_ref.PLUGINS):
         src = os.path.join(build_ref.OUT, "lib", p)
         if newer(os.path.join(libdir, p), [src]):
             shutil.copy(src, libdir)
     exe = os.path.join(bindir, "test_cuda_map")
     src = os.path.join(HERE, "test_cuda_map.cpp")
-    if newer(exe, [src, lib, os.path.join(ROOT, "tools", "bench_models.hpp")]):
-        subprocess.check_call([build_ref.CXX, "-O1", "-g"] + build_ref.public_flags() + ["-I" + os.path.join(ROOT, "oracle"),
-                              src, "-o", exe, "-L" + libdir, "-lcasadi", "-Wl,-rpath,$ORIGIN/../lib"])
+    if newer(exe, [src, lib, os.path.join(ROOT, "tools", "bench_models.hpp")] + hdrs):
+        # (the checker: oracle/_build/liboracle.so evaluates lowered tapes in the host-side checks)
+        sys.path.insert(0, ROOT)
+        import oracle
+        oracle.build_oracle()
+        odir = os.path.join(ROOT, "oracle", "_build")
+        subprocess.check_call([build_ref.CXX, "-O1", "-g"] + build_ref.public_flags() + ["-I" + os.path.join(ROOT, "oracle"), "-I" + HOST,
+                              "-I" + os.path.join(ref, "casadi", "core"),
+                              src, "-o", exe, "-L" + libdir, "-lcasadi", "-L" + odir, "-loracle",
+                              "-Wl,-rpath,$ORIGIN/../lib", "-Wl,-rpath,$ORIGIN/../../../../oracle/_build"])
     # the plugin benchmark (bench.py's end-to-end leg): same library, the reference's public API only
     bexe = os.path.join(bindir, "cuda_bench")
     bsrc = os.path.join(ROOT, "tools", "cuda_bench.cpp")

@@ -12,6 +12,7 @@
 #include <unistd.h>
 
 #include "models.hpp"
+#include <cuda_map.hpp>           // CudaMap::lowered_tape (new internal header, casadi_b200/host)
 #include <casadi/core/mapsum.hpp>  // MapSum::create (internal header of the reference: the class has no public factory with a parallelization argument)
 
 using namespace casadi;
@@ -110,6 +111,116 @@ static void host_side_checks() {
     threw = false;
     try { g.map(4, "cuda"); } catch (std::exception& e) { threw = std::string(e.what()).find("no device lowering") != std::string::npos; }
     CHECK(threw, "MX function with an unsupported node must be rejected");
+  }
+}
+
+// ---- the fixed-step integrator ("rk" plugin, casadi/solvers/runge_kutta.cpp) under a map.
+// The oracle (oracle/oracle.c, the checker) evaluates the tape CudaMap lowers the integrator to; the reference's own
+// Integrator::eval through f.map(n, "serial") is the expected result, bit for bit.
+extern "C" int oracle_map_eval(long long n_instr, const int* op, const int* i0, const int* i1, const int* i2, const double* d,
+                               long long n_in, const long long* nnz_in, long long n_out, const long long* nnz_out, long long N,
+                               const double* const* arg, double* const* res, double* w);
+
+static std::vector<std::vector<double>> eval_tape(const CudaMap::Tape& t, casadi_int n, const std::vector<std::vector<double>>& in) {
+  std::vector<std::vector<double>> out(t.nnz_out.size());
+  std::vector<const double*> arg(t.nnz_in.size());
+  std::vector<double*> res(t.nnz_out.size());
+  std::vector<long long> ni(t.nnz_in.begin(), t.nnz_in.end()), no(t.nnz_out.begin(), t.nnz_out.end());
+  for (size_t j = 0; j < arg.size(); ++j) arg[j] = ni[j] ? in.at(j).data() : nullptr;
+  for (size_t j = 0; j < res.size(); ++j) { out[j].assign(no[j] * n, -777.0); res[j] = out[j].data(); }
+  std::vector<double> w(t.sz_w + 1);
+  int flag = oracle_map_eval(static_cast<long long>(t.op.size()), t.op.data(), t.i0.data(), t.i1.data(), t.i2.data(), t.d.data(),
+                             static_cast<long long>(ni.size()), ni.data(), static_cast<long long>(no.size()), no.data(), n,
+                             arg.data(), res.data(), w.data());
+  CHECK(flag == 0, "oracle_map_eval returned " + str(flag));
+  return out;
+}
+
+// time-dependent ODE with a parameter, a control and a quadrature: x' = ((1-x1^2) x0 - x1 + u + sin t, p x0), q' = x.x + u^2 cos t
+static Function rk_integrator(const std::string& name, const std::vector<double>& tout, casadi_int nk, bool simplify = false) {
+  SX x = SX::sym("x", 2), p = SX::sym("p"), u = SX::sym("u"), t = SX::sym("t");
+  SX ode = vertcat((1 - x(1) * x(1)) * x(0) - x(1) + u + sin(t), p * x(0));
+  SX quad = dot(x, x) + u * u * cos(t);
+  SXDict dae = {{"x", x}, {"p", p}, {"u", u}, {"t", t}, {"ode", ode}, {"quad", quad}};
+  Dict opts = {{"number_of_finite_elements", nk}};
+  if (simplify) opts["simplify"] = true;
+  return integrator(name, "rk", dae, 0.25, tout, opts);
+}
+
+static std::vector<std::vector<double>> integrator_inputs(const Function& F, unsigned seed) {
+  auto in = random_inputs(F, seed, -0.8, 0.8);
+  // signed zeros and a repeated control: q = qf + 1.*q_prev must keep the reference's zero signs
+  if (!in[0].empty()) in[0][0] = -0.0;
+  return in;
+}
+
+static void check_bits(const std::vector<std::vector<double>>& got, const std::vector<std::vector<double>>& want, const std::string& what) {
+  CHECK(got.size() >= want.size(), what + ": output count");
+  for (size_t j = 0; j < want.size(); ++j) {
+    CHECK(got[j].size() == want[j].size(), what + ": size of output " + str(j));
+    if (got[j].size() != want[j].size()) continue;
+    CHECK(want[j].empty() || std::memcmp(got[j].data(), want[j].data(), want[j].size() * 8) == 0, what + ": output " + str(j) + " differs in bits");
+  }
+}
+
+static void integrator_lowering_checks() {
+  const casadi_int n = 64;
+  // one output time, several output times (3 intervals of different length: 7 finite elements become 2 + 3 + 3)
+  for (int variant = 0; variant < 2; ++variant) {
+    std::vector<double> tout = variant == 0 ? std::vector<double>{1.0} : std::vector<double>{0.4, 0.9, 1.35};
+    Function I = rk_integrator("intg" + str(variant), tout, 7);
+    CHECK(I.class_name() == "RungeKutta", I.class_name());
+    Function ref = I.map(n, "serial");
+    auto in = integrator_inputs(ref, 11 + variant);
+    auto want = eval(ref, in);
+    CudaMap::Tape t = CudaMap::lowered_tape(I);
+    check_bits(eval_tape(t, n, in), want, "lowered rk integrator, variant " + str(variant));
+    printf("rk integrator variant %d: lowered tape %zu instructions, xf[0] = %.17g, qf[last] = %.17g\n", variant, t.op.size(),
+           want[INTEGRATOR_XF][0], want[INTEGRATOR_QF].back());
+    // forward sensitivities: the augmented integrator (Integrator::get_forward) inside its MX wrapper
+    for (casadi_int nfwd : {1, 3}) {
+      Function dI = I.forward(nfwd);
+      Function dref = dI.map(n, "serial");
+      auto din = integrator_inputs(dref, 23 + variant);
+      auto dwant = eval(dref, din);
+      CudaMap::Tape dt = CudaMap::lowered_tape(dI);
+      check_bits(eval_tape(dt, n, din), dwant, "lowered forward(" + str(nfwd) + ") of the rk integrator, variant " + str(variant));
+    }
+  }
+  // the simplified form (FixedStepIntegrator::create_advanced, integrator.cpp:1894-1950) is a plain MX function that expands
+  {
+    Function I = rk_integrator("intg_simple", {1.0}, 5, true);
+    CHECK(I.class_name() == "MXFunction", I.class_name());
+    Function ref = I.map(n, "serial");
+    auto in = integrator_inputs(ref, 31);
+    check_bits(eval_tape(CudaMap::lowered_tape(I), n, in), eval(ref, in), "simplified rk integrator");
+  }
+  // adjoint sensitivities (backward states) are refused loudly
+  {
+    Function I = rk_integrator("intg_adj", {1.0}, 4);
+    bool threw = false;
+    try { CudaMap::lowered_tape(I.reverse(1)); } catch (std::exception& e) { threw = std::string(e.what()).find("no device lowering") != std::string::npos; }
+    CHECK(threw, "reverse mode of an integrator must be refused");
+  }
+}
+
+static void integrator_gpu_checks() {
+  for (casadi_int n : {3, 1000, 70000}) {
+    Function I = rk_integrator("intg_gpu", {0.4, 0.9, 1.35}, 7);
+    Function ref = I.map(n, "serial"), F = I.map(n, "cuda");
+    CHECK(F.class_name() == "CudaMap", F.class_name());
+    auto in = integrator_inputs(ref, 41);
+    check_bits(eval(F, in), eval(ref, in), "rk integrator under map(" + str(n) + ", cuda)");
+    if (n == 1000) {
+      Function dI = I.forward(2);
+      Function dref = dI.map(n, "serial"), dF = dI.map(n, "cuda");
+      auto din = integrator_inputs(dref, 43);
+      check_bits(eval(dF, din), eval(dref, din), "forward(2) of the rk integrator under map(cuda)");
+      // and the derivative of the map itself (Map::get_forward -> CudaMap over the augmented integrator)
+      Function Fd = F.forward(2), Rd = ref.forward(2);
+      auto fin = integrator_inputs(Rd, 47);
+      check_bits(eval(Fd, fin), eval(Rd, fin), "forward(2) of map(cuda) of the rk integrator");
+    }
   }
 }
 
@@ -398,7 +509,8 @@ int main(int argc, char** argv) {
   }
   try {
     host_side_checks();
-    if (no_gpu) no_gpu_checks(); else { gpu_checks(); kkt_checks(); }
+    integrator_lowering_checks();
+    if (no_gpu) no_gpu_checks(); else { gpu_checks(); kkt_checks(); integrator_gpu_checks(); }
   } catch (std::exception& e) {
     printf("FAIL: unexpected exception: %s\n", e.what());
     return 1;

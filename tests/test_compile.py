@@ -134,3 +134,12 @@ def test_degenerate_map_rejected():
 def test_empty_tape_and_zero_nnz_io():
     t = CudaTape(_mk([], [], [], [], [], 0, [0, 2], [0]), device=-1)
     assert t.info()["n_words"] == 1
+
+
+@pytest.mark.parametrize("nbytes,dmis,smis", [(0, 0, 0), (1, 0, 0), (4095, 3, 5), (300 << 10, 8, 0), (300 << 10, 24, 16),
+                                               ((5 << 20) + 1237, 8, 8), ((9 << 20) + 8, 0, 40), (64 << 20, 16, 0)])
+def test_host_staging_copy_is_exact(nbytes, dmis, smis):
+    """The multi-threaded streaming copy of the host path (csrc/hostcopy.cpp, CopyPool) moves exactly the bytes it is
+    given, whatever the alignment of the caller's buffer (a std::vector<double> is 16-byte aligned, a slice of one 8)."""
+    rate = capi.selftest_host_copy(nbytes, dmis, smis)
+    assert rate >= 0
