@@ -174,22 +174,28 @@ bool host_ptr_is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
-// staging of the host-pointer path (eval_host_impl): [slot] double buffering
+// staging of the host-pointer path (eval_host_impl): [slot] buffering
 struct HostPipe {
+  // Slots of the pipeline: chunk c is queued on the device, then the results of chunk c-(kSlots-1) are copied out of
+  // the pinned staging.  A third slot (chunk c+1 queued before the copy-out of chunk c-1) was measured and does not pay:
+  // with pageable caller buffers the host memory system is the limit -- the D2H DMA writes, the reads and the
+  // non-temporal writes of the staging copy share it -- and the D2H phase simply stretches (quadrotor Jacobian, 2e6
+  // instances: 50.1 ms with two slots, 52.0 ms with three; profiles/r2_e2e_staging.txt).
+  static constexpr int kSlots = 2;
   bool ready = false;
   cudaStream_t s[3] = {nullptr, nullptr, nullptr};  // H2D, compute, D2H
-  cudaEvent_t ev[2][3] = {};                        // per slot: H2D done, compute done, D2H done
-  std::vector<DevBuf> in_aos[2], in_soa[2], out_aos[2], out_soa[2];
+  cudaEvent_t ev[kSlots][3] = {};                   // per slot: H2D done, compute done, D2H done
+  std::vector<DevBuf> in_aos[kSlots], in_soa[kSlots], out_aos[kSlots], out_soa[kSlots];
   std::vector<DevBuf> bcast;  // reduce_in operands (one instance)
   DevBuf red;
   // pageable caller buffers go through pinned staging (the DMA engines cannot read pageable memory; the driver's own
   // staging of cudaMemcpyAsync is synchronous and serialises the pipeline)
-  std::vector<PinBuf> in_pin[2], out_pin[2];
+  std::vector<PinBuf> in_pin[kSlots], out_pin[kSlots];
   PinBuf red_pin;
-  cudaEvent_t tev[2][6] = {};  // per slot: start/stop of the H2D, compute and D2H phase (timing enabled)
-  bool tev_used[2] = {false, false};
+  cudaEvent_t tev[kSlots][6] = {};  // per slot: start/stop of the H2D, compute and D2H phase (timing enabled)
+  bool tev_used[kSlots] = {};
   void release() {
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kSlots; ++b) {
       for (auto* v : {&in_aos[b], &in_soa[b], &out_aos[b], &out_soa[b]}) for (auto& x : *v) x.release();
       for (auto* v : {&in_pin[b], &out_pin[b]}) for (auto& x : *v) x.release();
       for (int k = 0; k < 3; ++k) if (ev[b][k]) cudaEventDestroy(ev[b][k]);
@@ -901,7 +907,7 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
   };
   // copy the results of chunk c out of the pinned staging of its slot (after its D2H has completed)
   auto copy_out = [&](long long c) -> int {
-    const int b = static_cast<int>(c & 1);
+    const int b = static_cast<int>(c % HostPipe::kSlots);
     const long long i0 = c * C, n = std::min(C, N - i0);
     bool any = false;
     for (size_t j = 0; j < n_out; ++j) any = any || stage_out[j];
@@ -921,7 +927,7 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
     return 0;
   };
   for (long long c = 0; c < nchunks; ++c) {
-    const int b = static_cast<int>(c & 1);
+    const int b = static_cast<int>(c % HostPipe::kSlots);
     const long long i0 = c * C, n = std::min(C, N - i0);
     std::vector<const double*> d_arg(n_in, nullptr);
     std::vector<double*> d_res(n_out, nullptr);
@@ -931,7 +937,7 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
       bool any = false;
       for (size_t j = 0; j < n_in; ++j) any = any || stage_in[j];
       if (any) {
-        if (c >= 2) CCU_CUDA(cudaEventSynchronize(hp.ev[b][0]));
+        if (c >= HostPipe::kSlots) CCU_CUDA(cudaEventSynchronize(hp.ev[b][0]));
         const auto t0 = std::chrono::steady_clock::now();
         for (size_t j = 0; j < n_in; ++j) {
           if (!stage_in[j]) continue;
@@ -1027,10 +1033,12 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
     CCU_CUDA(cudaEventRecord(hp.tev[b][5], s_d2h));
     CCU_CUDA(cudaEventRecord(hp.ev[b][2], s_d2h));
     hp.tev_used[b] = true;
-    // ---- stage 4 (host): results of chunk c-1, pinned staging -> caller memory, while the device works on chunk c
-    if (c > 0 && copy_out(c - 1)) return 1;
+    // ---- stage 4 (host): results of chunk c-2, pinned staging -> caller memory, while the device works on chunks c-1
+    // and c (the output staging of slot b is rewritten by chunk c+3, issued after the copy-out of chunk c)
+    if (c >= HostPipe::kSlots - 1 && copy_out(c - (HostPipe::kSlots - 1))) return 1;
   }
-  if (nchunks > 0 && copy_out(nchunks - 1)) return 1;
+  for (long long c = std::max<long long>(0, nchunks - (HostPipe::kSlots - 1)); c < nchunks; ++c)
+    if (copy_out(c)) return 1;
   // reduced outputs: level-1 tree over the block sums, then a tiny D2H
   for (size_t j = 0; j < n_out && finish_reduce; ++j) {
     if (!is_rout(j) || !res[j] || t->nnz_out[j] == 0) continue;
@@ -1042,8 +1050,7 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
     CCU_CUDA(cudaStreamSynchronize(s_cmp));  // hp.red is reused by the next reduced output
     std::memcpy(res[j], hp.red_pin.p, static_cast<size_t>(nnz) * 8);
   }
-  harvest(0);
-  harvest(1);
+  for (int b = 0; b < HostPipe::kSlots; ++b) harvest(b);
   return 0;
 }
 
@@ -1058,11 +1065,11 @@ static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, doub
   HostPipe& hp = t->pipe;
   if (!hp.ready) {
     for (int k = 0; k < 3; ++k) CCU_CUDA(cudaStreamCreateWithFlags(&hp.s[k], cudaStreamNonBlocking));
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < HostPipe::kSlots; ++b) {
       for (int k = 0; k < 3; ++k) CCU_CUDA(cudaEventCreateWithFlags(&hp.ev[b][k], cudaEventDisableTiming));
       for (int k = 0; k < 6; ++k) CCU_CUDA(cudaEventCreate(&hp.tev[b][k]));
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < HostPipe::kSlots; ++b) {
       hp.in_aos[b].resize(n_in); hp.in_soa[b].resize(n_in); hp.out_aos[b].resize(n_out); hp.out_soa[b].resize(n_out);
       hp.in_pin[b].resize(n_in); hp.out_pin[b].resize(n_out);
     }
@@ -1070,7 +1077,7 @@ static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, doub
     hp.ready = true;
   }
   t->st_h2d_ms = t->st_kernel_ms = t->st_d2h_ms = t->st_stage_ms = t->st_wall_ms = t->st_staged_bytes = 0;
-  hp.tev_used[0] = hp.tev_used[1] = false;
+  for (int b = 0; b < HostPipe::kSlots; ++b) hp.tev_used[b] = false;
   const auto t0 = std::chrono::steady_clock::now();
   int rc = eval_host_chunks(t, N, arg, res, reduce_in, reduce_out, g_off, N_glob, finish_reduce, in_groups, out_groups);
   const std::string first_error = rc ? g_err : std::string();

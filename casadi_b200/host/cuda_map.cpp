@@ -529,11 +529,18 @@ namespace casadi {
     } else {
       // An MX function whose nodes all have an SX evaluation (mapaccum/fold towers, wrapped maps)
       // collapses to one SX tape ...
+      // (a wrapped non-MX function "expands" to an SX function that still calls it: OP_CALL is not an expansion)
+      bool expanded = false;
       try {
         sx_ = leaf_.expand();
+        expanded = true;
+        for (casadi_int k = 0; k < sx_.n_instructions() && expanded; ++k) expanded = sx_.instruction_id(k) != OP_CALL;
       } catch (std::exception& e) {
-        // ... anything else (e.g. a Linsol call, solve_impl.hpp:57-73: "eval_sx not defined") is lowered
-        // node by node through the tape builder; unsupported nodes raise from there
+        expanded = false;
+      }
+      if (!expanded) {
+        // ... anything else (a Linsol call, solve_impl.hpp:57-73: "eval_sx not defined"; a fixed-step integrator) is
+        // lowered node by node through the tape builder; unsupported nodes raise from there
         casadi_assert(lowerable_class(leaf_), "Map 'cuda': function '" + leaf_.name() + "' (" + leaf_.class_name()
                       + ") is neither an SX function, an MX function nor a fixed-step integrator");
         lower_mx();
@@ -598,7 +605,7 @@ namespace casadi {
     if (f.is_a("SXFunction")) return export_tape(f);
     try {
       return export_tape(f.expand());
-    } catch (std::exception& e) {
+    } catch (std::exception& e) {  // not expandable, or the expansion still holds a call (export_tape refuses OP_CALL)
       casadi_assert(lowerable_class(f), "Map 'cuda': function '" + f.name() + "' (" + f.class_name()
                     + ") is neither an SX function, an MX function nor a fixed-step integrator");
     }

@@ -137,10 +137,13 @@ static std::vector<std::vector<double>> eval_tape(const CudaMap::Tape& t, casadi
 }
 
 // time-dependent ODE with a parameter, a control and a quadrature: x' = ((1-x1^2) x0 - x1 + u + sin t, p x0), q' = x.x + u^2 cos t
-static Function rk_integrator(const std::string& name, const std::vector<double>& tout, casadi_int nk, bool simplify = false) {
+// (exact: + - * / only, so that the device result can be compared bit for bit; otherwise the device's sin/cos are within
+// 2 ulp of the host's libm and the comparison needs the tolerance of a composite tape)
+static Function rk_integrator(const std::string& name, const std::vector<double>& tout, casadi_int nk, bool simplify = false,
+                              bool exact = false) {
   SX x = SX::sym("x", 2), p = SX::sym("p"), u = SX::sym("u"), t = SX::sym("t");
-  SX ode = vertcat((1 - x(1) * x(1)) * x(0) - x(1) + u + sin(t), p * x(0));
-  SX quad = dot(x, x) + u * u * cos(t);
+  SX ode = vertcat((1 - x(1) * x(1)) * x(0) - x(1) + u + (exact ? t * t / (1 + t) : sin(t)), p * x(0));
+  SX quad = dot(x, x) + u * u * (exact ? 1 - t / 3 : cos(t));
   SXDict dae = {{"x", x}, {"p", p}, {"u", u}, {"t", t}, {"ode", ode}, {"quad", quad}};
   Dict opts = {{"number_of_finite_elements", nk}};
   if (simplify) opts["simplify"] = true;
@@ -187,6 +190,12 @@ static void integrator_lowering_checks() {
       check_bits(eval_tape(dt, n, din), dwant, "lowered forward(" + str(nfwd) + ") of the rk integrator, variant " + str(variant));
     }
   }
+  {
+    Function I = rk_integrator("intg_exact", {0.4, 0.9, 1.35}, 7, false, true);
+    Function ref = I.map(n, "serial");
+    auto in = integrator_inputs(ref, 17);
+    check_bits(eval_tape(CudaMap::lowered_tape(I), n, in), eval(ref, in), "lowered rk integrator, exact-class dynamics");
+  }
   // the simplified form (FixedStepIntegrator::create_advanced, integrator.cpp:1894-1950) is a plain MX function that expands
   {
     Function I = rk_integrator("intg_simple", {1.0}, 5, true);
@@ -204,9 +213,17 @@ static void integrator_lowering_checks() {
   }
 }
 
+static void check_close(const std::vector<std::vector<double>>& got, const std::vector<std::vector<double>>& want, double rtol,
+                        const std::string& what) {
+  double rel = 0;
+  compare(std::vector<std::vector<double>>(got.begin(), got.begin() + std::min(got.size(), want.size())), want, &rel);
+  CHECK(rel <= rtol, what + ": relative error " + str(rel));
+}
+
 static void integrator_gpu_checks() {
   for (casadi_int n : {3, 1000, 70000}) {
-    Function I = rk_integrator("intg_gpu", {0.4, 0.9, 1.35}, 7);
+    // exact-class dynamics: the device evaluation has the bits of Integrator::eval
+    Function I = rk_integrator("intg_gpu", {0.4, 0.9, 1.35}, 7, false, true);
     Function ref = I.map(n, "serial"), F = I.map(n, "cuda");
     CHECK(F.class_name() == "CudaMap", F.class_name());
     auto in = integrator_inputs(ref, 41);
@@ -220,6 +237,11 @@ static void integrator_gpu_checks() {
       Function Fd = F.forward(2), Rd = ref.forward(2);
       auto fin = integrator_inputs(Rd, 47);
       check_bits(eval(Fd, fin), eval(Rd, fin), "forward(2) of map(cuda) of the rk integrator");
+      // dynamics with sin/cos of the time: composite tolerance (the device's sin/cos are within 2 ulp of glibc's)
+      Function It = rk_integrator("intg_gpu_trig", {0.4, 0.9, 1.35}, 7);
+      Function tref = It.map(n, "serial"), tF = It.map(n, "cuda");
+      auto tin = integrator_inputs(tref, 53);
+      check_close(eval(tF, tin), eval(tref, tin), 1e-11, "rk integrator with sin/cos dynamics under map(cuda)");
     }
   }
 }
