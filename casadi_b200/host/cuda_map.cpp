@@ -5,6 +5,8 @@
 #include "integrator_impl.hpp"
 #include "linsol.hpp"
 #include "multiplication.hpp"
+#include "rootfinder_impl.hpp"
+#include <casadi/solvers/newton.hpp>  // option members of the Newton plugin class (layout only; nothing is linked)
 #include "mx_node.hpp"
 #include "solve.hpp"
 
@@ -51,6 +53,18 @@ namespace casadi {
                         const ccu_int*, ccu_int*, ccu_int, int, double, ccu_int*) = nullptr;
       int (*builder_mtimes)(void*, const ccu_int*, const ccu_int*, const ccu_int*, const ccu_int*, ccu_int*,
                             const ccu_int*) = nullptr;
+      // single-device entry points (the Newton driver keeps its state on the device between launches)
+      void* (*tape_create)(ccu_int, const int*, const int*, const int*, const int*, const double*, ccu_int,
+                           ccu_int, const ccu_int*, ccu_int, const ccu_int*, int) = nullptr;
+      void (*tape_destroy)(void*) = nullptr;
+      int (*eval_reduce_device)(void*, ccu_int, const double* const*, double* const*, const int*, const int*, int,
+                                void*) = nullptr;
+      int (*set_device)(int) = nullptr;
+      void* (*dev_malloc)(ccu_int) = nullptr;
+      int (*dev_free)(void*) = nullptr;
+      int (*memcpy_h2d)(void*, const void*, ccu_int, void*) = nullptr;
+      int (*memcpy_d2h)(void*, const void*, ccu_int, void*) = nullptr;
+      int (*stream_sync)(void*) = nullptr;
       ccu_int (*builder_select)(void*, ccu_int, ccu_int, ccu_int) = nullptr;
       ccu_int (*builder_export)(const void*, int*, int*, int*, int*, double*, ccu_int, ccu_int*) = nullptr;
     };
@@ -89,6 +103,15 @@ namespace casadi {
         lib.builder_ldl = reinterpret_cast<decltype(lib.builder_ldl)>(sym("ccu_builder_ldl"));
         lib.builder_qr = reinterpret_cast<decltype(lib.builder_qr)>(sym("ccu_builder_qr"));
         lib.builder_mtimes = reinterpret_cast<decltype(lib.builder_mtimes)>(sym("ccu_builder_mtimes"));
+        lib.tape_create = reinterpret_cast<decltype(lib.tape_create)>(sym("ccu_tape_create"));
+        lib.tape_destroy = reinterpret_cast<decltype(lib.tape_destroy)>(sym("ccu_tape_destroy"));
+        lib.eval_reduce_device = reinterpret_cast<decltype(lib.eval_reduce_device)>(sym("ccu_map_eval_reduce_device"));
+        lib.set_device = reinterpret_cast<decltype(lib.set_device)>(sym("ccu_set_device"));
+        lib.dev_malloc = reinterpret_cast<decltype(lib.dev_malloc)>(sym("ccu_malloc"));
+        lib.dev_free = reinterpret_cast<decltype(lib.dev_free)>(sym("ccu_free"));
+        lib.memcpy_h2d = reinterpret_cast<decltype(lib.memcpy_h2d)>(sym("ccu_memcpy_h2d"));
+        lib.memcpy_d2h = reinterpret_cast<decltype(lib.memcpy_d2h)>(sym("ccu_memcpy_d2h"));
+        lib.stream_sync = reinterpret_cast<decltype(lib.stream_sync)>(sym("ccu_stream_sync"));
         lib.builder_select = reinterpret_cast<decltype(lib.builder_select)>(sym("ccu_builder_select"));
         lib.builder_export = reinterpret_cast<decltype(lib.builder_export)>(sym("ccu_builder_export"));
         if (!ok) {
@@ -137,6 +160,36 @@ namespace casadi {
       static std::vector<ccu_int> pattern(const Sparsity& sp) {
         std::vector<casadi_int> c = sp.compress();
         return std::vector<ccu_int>(c.begin(), c.end());
+      }
+
+      // Linsol::nfact + solve on handles: A = nonzeros of the matrix, xs = right-hand sides on entry, solutions on return
+      void linsol_solve(const Linsol& ls, const Vals& A, Vals& xs, casadi_int nrhs, bool tr) {
+        const Sparsity& sp = ls.sparsity();
+        std::vector<ccu_int> spa = pattern(sp);
+        if (ls.plugin_name() == "ldl") {
+          // symbolic phase as in LinsolLdl::init (linsol_ldl.cpp:67-100, default options)
+          std::vector<casadi_int> p;
+          Sparsity lt = sp.ldl(p, true);
+          std::vector<ccu_int> splt = pattern(lt), pp(p.begin(), p.end());
+          casadi_assert(lib.builder_ldl(b, spa.data(), splt.data(), pp.data(), A.data(), xs.data(), nrhs, nullptr) == 0,
+                        "Map 'cuda': " + std::string(lib.last_error()));
+        } else if (ls.plugin_name() == "qr") {
+          // symbolic phase as in LinsolQr::init (linsol_qr.cpp:67-84, default options, eps = 1e-12)
+          Sparsity spv, spr;
+          std::vector<casadi_int> prinv, pc;
+          sp.qr_sparse(spv, spr, prinv, pc);
+          std::vector<ccu_int> v1 = pattern(spv), r1 = pattern(spr), pi(prinv.begin(), prinv.end()),
+                               pcc(pc.begin(), pc.end());
+          ccu_int nullity = -1;
+          casadi_assert(lib.builder_qr(b, spa.data(), v1.data(), r1.data(), pi.data(), pcc.data(), A.data(), xs.data(),
+                                       nrhs, tr ? 1 : 0, 1e-12, &nullity) == 0,
+                        "Map 'cuda': " + std::string(lib.last_error()));
+          ccu_int bad = op(OP_NE, nullity, cst(0.));
+          fail_count = fail_count < 0 ? bad : op(OP_ADD, fail_count, bad);
+        } else {
+          casadi_error("Map 'cuda': linear solver plugin '" + ls.plugin_name()
+                       + "' has no device implementation (supported: ldl, qr)");
+        }
       }
 
       // Inline an SX function: replay its tape (sx_function.cpp:111-124) over handles
@@ -210,34 +263,7 @@ namespace casadi {
             if (auto* n1 = dynamic_cast<const LinsolCall<true>*>(x.get())) ls = &n1->linsol_;
             casadi_assert(ls != nullptr, "Map 'cuda': " + x.class_name() + " is not a Linsol call");
             Vals xs = W(in.at(0));  // right-hand sides, overwritten by the solutions (solve_impl.hpp:60)
-            const Vals& A = W(in.at(1));
-            const Sparsity& sp = ls->sparsity();
-            casadi_int nrhs = x.dep(0).size2();
-            std::vector<ccu_int> spa = pattern(sp);
-            if (ls->plugin_name() == "ldl") {
-              // symbolic phase as in LinsolLdl::init (linsol_ldl.cpp:67-100, default options)
-              std::vector<casadi_int> p;
-              Sparsity lt = sp.ldl(p, true);
-              std::vector<ccu_int> splt = pattern(lt), pp(p.begin(), p.end());
-              casadi_assert(lib.builder_ldl(b, spa.data(), splt.data(), pp.data(), A.data(), xs.data(), nrhs, nullptr) == 0,
-                            "Map 'cuda': " + std::string(lib.last_error()));
-            } else if (ls->plugin_name() == "qr") {
-              // symbolic phase as in LinsolQr::init (linsol_qr.cpp:67-84, default options, eps = 1e-12)
-              Sparsity spv, spr;
-              std::vector<casadi_int> prinv, pc;
-              sp.qr_sparse(spv, spr, prinv, pc);
-              std::vector<ccu_int> v1 = pattern(spv), r1 = pattern(spr), pi(prinv.begin(), prinv.end()),
-                                   pcc(pc.begin(), pc.end());
-              ccu_int nullity = -1;
-              casadi_assert(lib.builder_qr(b, spa.data(), v1.data(), r1.data(), pi.data(), pcc.data(), A.data(), xs.data(),
-                                           nrhs, tr ? 1 : 0, 1e-12, &nullity) == 0,
-                            "Map 'cuda': " + std::string(lib.last_error()));
-              ccu_int bad = op(OP_NE, nullity, cst(0.));
-              fail_count = fail_count < 0 ? bad : op(OP_ADD, fail_count, bad);
-            } else {
-              casadi_error("Map 'cuda': linear solver plugin '" + ls->plugin_name()
-                           + "' has no device implementation (supported: ldl, qr)");
-            }
+            linsol_solve(*ls, W(in.at(1)), xs, x.dep(0).size2(), tr);
             w[out.at(0)] = xs;
           } else if (o == OP_CALL) {
             Function fc = x.which_function();
@@ -407,10 +433,10 @@ namespace casadi {
   } // namespace
 
   CudaMap::CudaMap(const std::string& name, const Function& f, casadi_int n)
-    : Map(name, f, n), rep_(1), flatten_(true), device_(0), builder_(nullptr), has_flag_(false) {
+    : Map(name, f, n), rep_(1), flatten_(true), device_(0), builder_(nullptr), has_flag_(false), newton_(false) {
   }
 
-  CudaMap::CudaMap(DeserializingStream& s) : Map(s), rep_(1), flatten_(true), device_(0), builder_(nullptr), has_flag_(false) {
+  CudaMap::CudaMap(DeserializingStream& s) : Map(s), rep_(1), flatten_(true), device_(0), builder_(nullptr), has_flag_(false), newton_(false) {
     s.unpack("CudaMap::in_groups", in_groups_);
     s.unpack("CudaMap::out_groups", out_groups_);
     s.unpack("CudaMap::flatten", flatten_);
@@ -524,6 +550,15 @@ namespace casadi {
       rep_ *= inf.at("n").to_int();
       leaf_ = inf.at("f").to_function();
     }
+    newton_ = is_newton(leaf_);
+    if (newton_) {
+      // data-dependent iteration: two tapes driven from the host over device-resident state (NewtonPlan)
+      newton_plan_ = newton_plan(leaf_);
+      tape_ = Tape();
+      for (casadi_int j=0; j<leaf_.n_in(); ++j) tape_.nnz_in.push_back(leaf_.nnz_in(j));
+      for (casadi_int j=0; j<leaf_.n_out(); ++j) tape_.nnz_out.push_back(leaf_.nnz_out(j));
+      return;
+    }
     if (leaf_.is_a("SXFunction")) {
       sx_ = leaf_;
     } else {
@@ -625,6 +660,297 @@ namespace casadi {
     return t;
   }
 
+  // ------------------------------------------------------------------------------------------------
+  // Newton rootfinder under the map (see NewtonPlan in cuda_map.hpp)
+  // ------------------------------------------------------------------------------------------------
+  namespace {
+    // The option members of the plugin class are protected; a pointer to member formed in a derived scope has the type
+    // `T Newton::*` and reads them from any Newton (no object of this type ever exists, nothing of the plugin is linked)
+    struct NewtonOptions : public Newton {
+      static casadi_int max_iter(const Newton* p) { return p->*(&NewtonOptions::max_iter_); }
+      static double abstol(const Newton* p) { return p->*(&NewtonOptions::abstol_); }
+      static double abstol_step(const Newton* p) { return p->*(&NewtonOptions::abstolStep_); }
+      static bool line_search(const Newton* p) { return p->*(&NewtonOptions::line_search_); }
+    };
+
+    CudaMap::Tape export_builder(CudaLib& lib, void* b, const std::vector<casadi_int>& nnz_in,
+                                 const std::vector<casadi_int>& nnz_out) {
+      CudaMap::Tape t;
+      ccu_int sz_w = 0;
+      ccu_int n = lib.builder_export(b, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &sz_w);
+      t.op.resize(n); t.i0.resize(n); t.i1.resize(n); t.i2.resize(n); t.d.resize(n);
+      lib.builder_export(b, get_ptr(t.op), get_ptr(t.i0), get_ptr(t.i1), get_ptr(t.i2), get_ptr(t.d), n, &sz_w);
+      t.sz_w = sz_w;
+      t.nnz_in = nnz_in;
+      t.nnz_out = nnz_out;
+      return t;
+    }
+  } // namespace
+
+  bool CudaMap::is_newton(const Function& f) {
+    return f.class_name() == "Newton" && dynamic_cast<const Rootfinder*>(f.get()) != nullptr;
+  }
+
+  CudaMap::NewtonPlan CudaMap::newton_plan(const Function& rf) {
+    casadi_assert(is_newton(rf), "Map 'cuda': '" + rf.name() + "' is not a Newton rootfinder");
+    CudaLib& lib = cuda_lib();
+    casadi_assert(lib.handle!=nullptr, "Map 'cuda': " + lib.error);
+    const Rootfinder* R = dynamic_cast<const Rootfinder*>(rf.get());
+    const Newton* Nw = static_cast<const Newton*>(R);
+    NewtonPlan P;
+    P.name = rf.name();
+    P.n = R->n_; P.iin = R->iin_; P.iout = R->iout_;
+    P.max_iter = NewtonOptions::max_iter(Nw);
+    P.line_search = NewtonOptions::line_search(Nw);
+    P.error_on_fail = R->error_on_fail_;
+    const double abstol = NewtonOptions::abstol(Nw), abstol_step = NewtonOptions::abstol_step(Nw);
+    const double inf = std::numeric_limits<double>::infinity();
+    casadi_assert(P.max_iter >= 1, "Map 'cuda': Newton rootfinder '" + rf.name() + "' with max_iter < 1");
+    const casadi_int n = P.n, n_in = rf.n_in(), n_out = rf.n_out();
+    for (casadi_int j = 0; j < n_in; ++j) P.nnz_in.push_back(rf.nnz_in(j));
+    for (casadi_int j = 0; j < n_out; ++j) { P.nnz_out.push_back(rf.nnz_out(j)); if (j != P.iout) P.aux.push_back(j); }
+    casadi_assert(rf.nnz_in(P.iin) == n && rf.nnz_out(P.iout) == n, "Map 'cuda': Newton rootfinder with a sparse unknown");
+    const Function& jac = R->get_function("jac_g_x");
+    const Function& g = R->get_function("g");
+    // tape signature (both tapes)
+    std::vector<casadi_int> t_in = P.nnz_in, t_out;
+    t_in.push_back(n); t_in.push_back(NEWTON_SC);
+    for (casadi_int j : P.aux) t_in.push_back(P.nnz_out[j]);
+    t_out.push_back(n); t_out.push_back(n); t_out.push_back(NEWTON_SC);
+    for (casadi_int j : P.aux) t_out.push_back(P.nnz_out[j]);
+    t_out.push_back(NEWTON_COUNTS);
+    for (int which = 0; which < 2; ++which) {
+      Lowering L(lib);
+      try {
+        auto sel = [&](ccu_int c, ccu_int a, ccu_int b2) {
+          ccu_int h = lib.builder_select(L.b, c, a, b2);
+          casadi_assert(h >= 0, "Map 'cuda': " + std::string(lib.last_error()));
+          return h;
+        };
+        std::vector<Vals> in(t_in.size());
+        for (size_t j = 0; j < t_in.size(); ++j) {
+          in[j].resize(t_in[j]);
+          for (casadi_int e = 0; e < t_in[j]; ++e) in[j][e] = lib.builder_input(L.b, static_cast<ccu_int>(j), e);
+        }
+        const Vals& X = in[P.iin];
+        const Vals& DX = in[n_in];
+        const Vals& SC = in[n_in + 1];
+        const ccu_int zero = L.cst(0.), one = L.cst(1.);
+        const ccu_int sc_abstol = SC[0], sc_step = SC[1], sc_alpha = SC[2], sc_active = SC[3], sc_ls = SC[4], sc_failed = SC[5];
+        Vals Xn(n), DXn(n), SCn(NEWTON_SC), CNT(NEWTON_COUNTS);
+        std::vector<Vals> aux_new(P.aux.size());
+        if (which == 0) {
+          // ---- Newton direction (newton.cpp:152-196): jac_g_x at X, max|F| test, factorise + solve, step test
+          std::vector<const Vals*> a(n_in, nullptr);
+          for (casadi_int j = 0; j < n_in; ++j) a[j] = &in[j];
+          std::vector<Vals> r(jac.n_out());
+          std::vector<Vals*> rp(jac.n_out(), nullptr);
+          for (casadi_int j = 0; j < jac.n_out(); ++j) { r[j].assign(jac.nnz_out(j), zero); rp[j] = &r[j]; }
+          L.call(jac, a, rp);
+          const Vals& J = r[0];
+          const Vals& F = r[1 + P.iout];
+          ccu_int abst = zero, conv1 = zero;
+          if (abstol != inf) {
+            for (casadi_int i = 0; i < n; ++i) {  // abstol = std::max(abstol, fabs(f[i])): (a < b) ? b : a
+              ccu_int fa = L.op(OP_FABS, F[i]);
+              abst = sel(L.op(OP_LT, abst, fa), fa, abst);
+            }
+            conv1 = L.op(OP_LE, abst, L.cst(abstol));
+          }
+          Vals dx = F;
+          L.linsol_solve(R->linsol_, J, dx, 1, false);
+          const ccu_int singular = L.fail_count >= 0 ? L.fail_count : zero;
+          L.fail_count = -1;
+          ccu_int st = zero, conv2 = zero;
+          if (abstol_step != inf) {
+            for (casadi_int i = 0; i < n; ++i) {
+              ccu_int fa = L.op(OP_FABS, dx[i]);
+              st = sel(L.op(OP_LT, st, fa), fa, st);
+            }
+            conv2 = L.op(OP_LE, st, L.cst(abstol_step));
+          }
+          const ccu_int act = sc_active;
+          const ccu_int cont = L.op(OP_AND, act, L.op(OP_NOT, L.op(OP_OR, conv1, conv2)));  // iterates on after this phase
+          const ccu_int upd = L.op(OP_AND, act, L.op(OP_NOT, conv1));                        // reached the linear solve
+          const ccu_int minus_one = L.cst(-1.);
+          for (casadi_int i = 0; i < n; ++i) {
+            // without line search: casadi_axpy(n, -alpha, f, x) with alpha = 1
+            Xn[i] = P.line_search ? X[i] : sel(cont, L.op(OP_ADD, X[i], L.op(OP_MUL, minus_one, dx[i])), X[i]);
+            DXn[i] = sel(upd, dx[i], DX[i]);
+          }
+          SCn[0] = sel(act, abst, sc_abstol);
+          SCn[1] = sel(upd, st, sc_step);
+          SCn[2] = sel(cont, one, sc_alpha);
+          SCn[3] = cont;
+          SCn[4] = P.line_search ? cont : zero;
+          SCn[5] = sc_failed;
+          for (size_t k = 0; k < P.aux.size(); ++k) {
+            const Vals& old = in[n_in + 2 + k];
+            const Vals& nw = r[1 + P.aux[k]];
+            aux_new[k].resize(old.size());
+            for (size_t e = 0; e < old.size(); ++e) aux_new[k][e] = sel(act, nw[e], old[e]);
+          }
+          CNT[0] = SCn[3]; CNT[1] = SCn[4]; CNT[2] = L.op(OP_AND, upd, singular); CNT[3] = SCn[5];
+        } else {
+          // ---- one line-search trial (newton.cpp:199-221): x_trial = x - alpha*dx, g, acceptance, give up or halve alpha
+          Vals xt(n);
+          const ccu_int na = L.op(OP_NEG, sc_alpha);
+          for (casadi_int i = 0; i < n; ++i) xt[i] = L.op(OP_ADD, X[i], L.op(OP_MUL, na, DX[i]));
+          std::vector<const Vals*> a(n_in, nullptr);
+          for (casadi_int j = 0; j < n_in; ++j) a[j] = j == P.iin ? &xt : &in[j];
+          std::vector<Vals> r(g.n_out());
+          std::vector<Vals*> rp(g.n_out(), nullptr);
+          for (casadi_int j = 0; j < g.n_out(); ++j) { r[j].assign(g.nnz_out(j), zero); rp[j] = &r[j]; }
+          L.call(g, a, rp);
+          casadi_assert(L.fail_count < 0, "Map 'cuda': linear solves inside the residual function of a rootfinder");
+          const Vals& Ft = r[P.iout];
+          ccu_int nt = zero;  // casadi_norm_inf: fmax(ret, fabs(x))
+          for (casadi_int i = 0; i < n; ++i) nt = L.op(OP_FMAX, nt, L.op(OP_FABS, Ft[i]));
+          const ccu_int thr = L.op(OP_MUL, L.op(OP_SUB, one, L.op(OP_DIV, sc_alpha, L.cst(2.))), sc_abstol);
+          const ccu_int accept = L.op(OP_LE, nt, thr);
+          const ccu_int limit = L.op(OP_LE, L.op(OP_MUL, sc_alpha, sc_step), L.cst(abstol_step));
+          const ccu_int giveup = L.op(OP_AND, L.op(OP_NOT, accept), limit);
+          const ccu_int acc = L.op(OP_AND, sc_ls, accept), gv = L.op(OP_AND, sc_ls, giveup);
+          const ccu_int ls_next = L.op(OP_AND, sc_ls, L.op(OP_AND, L.op(OP_NOT, accept), L.op(OP_NOT, giveup)));
+          for (casadi_int i = 0; i < n; ++i) { Xn[i] = sel(acc, xt[i], X[i]); DXn[i] = DX[i]; }
+          SCn[0] = sc_abstol;
+          SCn[1] = sc_step;
+          SCn[2] = sel(ls_next, L.op(OP_MUL, sc_alpha, L.cst(0.5)), sc_alpha);
+          SCn[3] = L.op(OP_AND, sc_active, L.op(OP_NOT, gv));
+          SCn[4] = ls_next;
+          SCn[5] = L.op(OP_OR, sc_failed, gv);
+          for (size_t k = 0; k < P.aux.size(); ++k) {
+            const Vals& old = in[n_in + 2 + k];
+            const Vals& nw = r[P.aux[k]];
+            aux_new[k].resize(old.size());
+            for (size_t e = 0; e < old.size(); ++e) aux_new[k][e] = sel(sc_ls, nw[e], old[e]);
+          }
+          CNT[0] = SCn[3]; CNT[1] = SCn[4]; CNT[2] = zero; CNT[3] = SCn[5];
+        }
+        ccu_int o = 0;
+        for (casadi_int i = 0; i < n; ++i) lib.builder_output(L.b, o, i, Xn[i]);
+        ++o;
+        for (casadi_int i = 0; i < n; ++i) lib.builder_output(L.b, o, i, DXn[i]);
+        ++o;
+        for (casadi_int i = 0; i < NEWTON_SC; ++i) lib.builder_output(L.b, o, i, SCn[i]);
+        ++o;
+        for (size_t k = 0; k < P.aux.size(); ++k, ++o)
+          for (size_t e = 0; e < aux_new[k].size(); ++e) lib.builder_output(L.b, o, static_cast<ccu_int>(e), aux_new[k][e]);
+        for (casadi_int i = 0; i < NEWTON_COUNTS; ++i) lib.builder_output(L.b, o, i, CNT[i]);
+        P.tape[which] = export_builder(lib, L.b, t_in, t_out);
+      } catch (...) {
+        lib.builder_destroy(L.b);
+        throw;
+      }
+      lib.builder_destroy(L.b);
+    }
+    return P;
+  }
+
+  int CudaMap::newton_run(const NewtonPlan& P, casadi_int N, const double* const* arg, double* const* res, NewtonBackend& be,
+                          casadi_int* n_failed, casadi_int* n_singular, casadi_int launches[2]) {
+    const casadi_int n_in = static_cast<casadi_int>(P.nnz_in.size()), n_aux = static_cast<casadi_int>(P.aux.size());
+    std::vector<double*> owned;
+    auto get = [&](casadi_int count) { double* p = count > 0 ? be.alloc(count) : nullptr; if (p) owned.push_back(p); return p; };
+    // inputs other than the unknown: constant during the solve (a null argument reads as zeros in the tape)
+    std::vector<const double*> fixed(n_in, nullptr);
+    for (casadi_int j = 0; j < n_in; ++j) {
+      if (j == P.iin || !arg[j] || P.nnz_in[j] == 0) continue;
+      double* d = get(N * P.nnz_in[j]);
+      be.upload(d, arg[j], N * P.nnz_in[j]);
+      fixed[j] = d;
+    }
+    // state, double buffered: a launch reads one copy and writes the other
+    double *X[2], *DX[2], *SC[2];
+    std::vector<double*> AUX[2];
+    for (int b = 0; b < 2; ++b) {
+      X[b] = get(N * P.n); DX[b] = get(N * P.n); SC[b] = get(N * NEWTON_SC);
+      for (casadi_int k = 0; k < n_aux; ++k) AUX[b].push_back(get(N * P.nnz_out[P.aux[k]]));
+    }
+    be.upload(X[0], arg[P.iin], N * P.n);  // the initial guess (null: zeros)
+    be.upload(DX[0], nullptr, N * P.n);
+    {
+      std::vector<double> sc0(N * NEWTON_SC, 0.);
+      for (casadi_int i = 0; i < N; ++i) { sc0[i * NEWTON_SC + 2] = 1.; sc0[i * NEWTON_SC + 3] = 1.; }
+      be.upload(SC[0], get_ptr(sc0), N * NEWTON_SC);
+    }
+    for (casadi_int k = 0; k < n_aux; ++k) if (AUX[0][k]) be.upload(AUX[0][k], nullptr, N * P.nnz_out[P.aux[k]]);
+    int cur = 0, flag = 0;
+    double counts[NEWTON_COUNTS] = {static_cast<double>(N), 0, 0, 0};
+    launches[0] = launches[1] = 0;
+    auto launch = [&](int which) {
+      std::vector<const double*> a(fixed);
+      a[P.iin] = X[cur];
+      a.push_back(DX[cur]); a.push_back(SC[cur]);
+      for (casadi_int k = 0; k < n_aux; ++k) a.push_back(AUX[cur][k]);
+      std::vector<double*> r = {X[1 - cur], DX[1 - cur], SC[1 - cur]};
+      for (casadi_int k = 0; k < n_aux; ++k) r.push_back(AUX[1 - cur][k]);
+      r.push_back(nullptr);  // the counts: placed by the backend
+      int f = be.launch(which, N, a, r, counts);
+      cur = 1 - cur;
+      launches[which]++;
+      return f;
+    };
+    casadi_int singular = 0;
+    for (casadi_int iter = 0; iter < P.max_iter && counts[0] > 0 && !flag; ++iter) {
+      flag = launch(0);
+      singular += static_cast<casadi_int>(counts[2]);
+      while (!flag && counts[1] > 0) flag = launch(1);
+    }
+    if (!flag) {
+      if (res[P.iout]) be.download(res[P.iout], X[cur], N * P.n);
+      for (casadi_int k = 0; k < n_aux; ++k)
+        if (res[P.aux[k]] && AUX[cur][k]) be.download(res[P.aux[k]], AUX[cur][k], N * P.nnz_out[P.aux[k]]);
+    }
+    for (double* p : owned) be.release(p);
+    // failed: the line search gave up, or still iterating after max_iter iterations (newton.cpp:143-149)
+    *n_failed = static_cast<casadi_int>(counts[3] + counts[0]);
+    *n_singular = singular;
+    if (flag) return flag;
+    return (P.error_on_fail && *n_failed > 0) || singular > 0 ? 1 : 0;
+  }
+
+  namespace {
+    // the state on the device, the tapes evaluated by ccu_map_eval_reduce_device (AoS), the counts through a 4-double buffer
+    struct NewtonDevice : public CudaMap::NewtonBackend {
+      CudaLib& lib;
+      void* tape[2];
+      double* d_counts = nullptr;
+      std::string error;
+      NewtonDevice(CudaLib& l, void* t0, void* t1) : lib(l) { tape[0] = t0; tape[1] = t1; d_counts = alloc(CudaMap::NEWTON_COUNTS); }
+      ~NewtonDevice() override { if (d_counts) lib.dev_free(d_counts); }
+      double* alloc(casadi_int n) override {
+        void* p = lib.dev_malloc(static_cast<ccu_int>(n) * 8);
+        casadi_assert(p != nullptr, "Map 'cuda': " + std::string(lib.last_error()));
+        return static_cast<double*>(p);
+      }
+      void release(double* p) override { lib.dev_free(p); }
+      void upload(double* dst, const double* src, casadi_int n) override {
+        if (n <= 0) return;
+        std::vector<double> z;
+        if (!src) { z.assign(n, 0.); src = get_ptr(z); }
+        casadi_assert(lib.memcpy_h2d(dst, src, static_cast<ccu_int>(n) * 8, nullptr) == 0 && lib.stream_sync(nullptr) == 0,
+                      "Map 'cuda': " + std::string(lib.last_error()));
+      }
+      void download(double* dst, const double* src, casadi_int n) override {
+        if (n <= 0) return;
+        casadi_assert(lib.memcpy_d2h(dst, src, static_cast<ccu_int>(n) * 8, nullptr) == 0 && lib.stream_sync(nullptr) == 0,
+                      "Map 'cuda': " + std::string(lib.last_error()));
+      }
+      int launch(int which, casadi_int N, const std::vector<const double*>& arg, const std::vector<double*>& res,
+                 double* counts) override {
+        // outputs: X, DX, SC, aux..., counts -- only the last is summed over the instances
+        std::vector<double*> r(res);
+        r.back() = d_counts;
+        std::vector<int> red(r.size(), 0);
+        red.back() = 1;
+        if (lib.eval_reduce_device(tape[which], N, get_ptr(arg), get_ptr(r), nullptr, get_ptr(red), 0 /* CCU_LAYOUT_AOS */, nullptr)) return 1;
+        if (lib.memcpy_d2h(counts, d_counts, CudaMap::NEWTON_COUNTS * 8, nullptr) || lib.stream_sync(nullptr)) return 1;
+        return 0;
+      }
+    };
+  } // namespace
+
   void CudaMap::init(const Dict& opts) {
     // Map::create passes an empty Dict (map.cpp:43-47): the devices come from the environment.
     //   CASADI_CUDA_DEVICE=k          one device (default 0)
@@ -668,6 +994,19 @@ namespace casadi {
     casadi_assert(lib.handle!=nullptr, "Map 'cuda': " + lib.error);
     const Tape& t = tape_;
     std::vector<int> dv = devices_.empty() ? std::vector<int>{device_} : devices_;
+    if (newton_) {
+      casadi_assert(dv.size() == 1, "Map 'cuda': a mapped Newton rootfinder runs on one device (CASADI_CUDA_DEVICE)");
+      for (int k = 0; k < 2; ++k) {
+        const Tape& tk = newton_plan_.tape[k];
+        m->newton_tape[k] = lib.tape_create(static_cast<ccu_int>(tk.op.size()), get_ptr(tk.op), get_ptr(tk.i0), get_ptr(tk.i1),
+                                            get_ptr(tk.i2), get_ptr(tk.d), tk.sz_w, static_cast<ccu_int>(tk.nnz_in.size()),
+                                            get_ptr(tk.nnz_in), static_cast<ccu_int>(tk.nnz_out.size()), get_ptr(tk.nnz_out), dv[0]);
+        casadi_assert(m->newton_tape[k]!=nullptr, "Map 'cuda': cannot put rootfinder '" + f_.name() + "' on device "
+                      + str(dv[0]) + ": " + std::string(lib.last_error()));
+      }
+      m->add_stat("cuda");
+      return 0;
+    }
     if (builder_) {
       m->tape = lib.builder_finish_multi(builder_, static_cast<ccu_int>(t.nnz_in.size()), get_ptr(t.nnz_in),
                                          static_cast<ccu_int>(t.nnz_out.size()), get_ptr(t.nnz_out),
@@ -694,6 +1033,7 @@ namespace casadi {
   void CudaMap::free_mem(void *mem) const {
     auto m = static_cast<CudaMapMemory*>(mem);
     if (m->tape) cuda_lib().multi_destroy(m->tape);
+    for (int k = 0; k < 2; ++k) if (m->newton_tape[k]) cuda_lib().tape_destroy(m->newton_tape[k]);
     delete m;
   }
 
@@ -707,6 +1047,28 @@ namespace casadi {
     CudaLib& lib = cuda_lib();
     m->stats_available = true;  // F.stats() reports the timers of the last call (function_internal.cpp:3168-3175)
     m->fstats.at("cuda").tic();
+    if (newton_) {
+      casadi_assert(reduce_in.empty() && reduce_out.empty() && in_groups_.empty() && out_groups_.empty(),
+                    "Map 'cuda': reductions and derivative layouts are not available for a mapped rootfinder");
+      std::vector<int> dv = devices_.empty() ? std::vector<int>{device_} : devices_;
+      casadi_assert(lib.set_device(dv[0]) == 0, "Map 'cuda': " + std::string(lib.last_error()));
+      casadi_int n_failed = 0, n_singular = 0, launches[2] = {0, 0};
+      int flag;
+      {
+        NewtonDevice be(lib, m->newton_tape[0], m->newton_tape[1]);
+        flag = newton_run(newton_plan_, n_*rep_, arg, res, be, &n_failed, &n_singular, launches);
+      }
+      m->fstats.at("cuda").toc();
+      // Rootfinder::eval raises when an instance failed and error_on_fail is set (rootfinder.cpp:294-296); a singular
+      // Jacobian makes Linsol::nfact fail (linsol_qr.cpp:146-163)
+      casadi_assert(n_singular == 0, "Map 'cuda': the Jacobian of rootfinder '" + leaf_.name() + "' is numerically singular for "
+                    + str(n_singular) + " instance(s)");
+      if (n_failed > 0 && newton_plan_.error_on_fail)
+        casadi_error("rootfinder process failed for " + str(n_failed) + " of " + str(n_*rep_) + " instances of '" + leaf_.name()
+                     + "'. Set 'error_on_fail' option to false to ignore this error.");
+      if (flag) casadi_warning("Map 'cuda' evaluation of '" + f_.name() + "' failed: " + std::string(lib.last_error()));
+      return flag;
+    }
     // Same contract as Map::eval_gen (map.cpp:141-157): instance i of input j is arg[j]+i*nnz_in(j);
     // null arg[j] reads as zero, null res[j] is not computed.  With reductions (MapSum::eval_gen, mapsum.cpp:154-186):
     // a reduced input is ONE instance read by all, a reduced output is the sum over the instances.

@@ -25,7 +25,8 @@ namespace casadi {
       (function_internal.hpp:184-194). */
   struct CASADI_EXPORT CudaMapMemory : public FunctionMemory {
     void* tape;  // ccu_multi*: the compiled tape on every device of the map
-    CudaMapMemory() : tape(nullptr) {}
+    void* newton_tape[2];  // ccu_tape*: direction and line-search tapes of a mapped Newton rootfinder
+    CudaMapMemory() : tape(nullptr) { newton_tape[0] = newton_tape[1] = nullptr; }
   };
 
   class CASADI_EXPORT CudaMap : public Map {
@@ -92,6 +93,47 @@ namespace casadi {
         of one nonzero is present when the lowering counts failed QR factorisations. */
     static Tape lowered_tape(const Function& f);
 
+    /** The Newton rootfinder under the map (casadi/solvers/newton.cpp:130-246).  Newton::solve has a data
+        dependent iteration count and line search per instance, so it is not one straight-line tape: it is two --
+        tape 0, the Newton direction (jac_g_x, convergence test on max|F|, Linsol factorise + solve, test on the step),
+        and tape 1, one line-search trial (x - alpha*dx, g, acceptance test, alpha halved) -- each evaluated for ALL
+        instances per launch with the instance's progress flags as data: an instance that has finished, or is not in
+        the phase the launch belongs to, keeps every value (bit-exact select).  The host only counts: after every
+        launch it reads the sums of the flags (a reduce_out output) and decides whether another line-search trial or
+        another Newton iteration is needed, up to max_iter.  All arithmetic of the solver runs on the device in the
+        reference's order, so every instance gets the bits Newton::solve gives it.
+        State of an instance (AoS, one array each): the iterate X (stored in the rootfinder input iin), the step DX,
+        the scalars SC = (abstol, abstolStep, alpha, active, in_line_search, failed), the auxiliary outputs. */
+    struct NewtonPlan {
+      Tape tape[2];          // inputs: the rootfinder's inputs (iin carries X), DX, SC, aux...; outputs: X, DX, SC, aux..., counts
+      casadi_int n = 0, iin = 0, iout = 0, max_iter = 0;
+      bool line_search = true, error_on_fail = true;
+      std::vector<casadi_int> nnz_in, nnz_out;  // of the rootfinder
+      std::vector<casadi_int> aux;              // the rootfinder outputs other than iout, in order
+      std::string name;
+    };
+    enum { NEWTON_SC = 6, NEWTON_COUNTS = 4 };  // counts: active, in line search, singular Jacobians, failed
+    /** Where the state lives and how a tape is evaluated over it: the device (CudaMap::eval) or, in the host-side
+        checks, plain arrays evaluated by the oracle. */
+    struct NewtonBackend {
+      virtual ~NewtonBackend() {}
+      virtual double* alloc(casadi_int n_doubles) = 0;
+      virtual void release(double* p) = 0;
+      virtual void upload(double* dst, const double* src, casadi_int n) = 0;  // src == nullptr: zeros
+      virtual void download(double* dst, const double* src, casadi_int n) = 0;
+      /// evaluate tape `which` over N instances (AoS arrays; a null array reads as zeros / is not written); the last
+      /// output -- res.back(), null on entry -- is the counts: summed over the instances into counts[NEWTON_COUNTS]
+      virtual int launch(int which, casadi_int N, const std::vector<const double*>& arg, const std::vector<double*>& res,
+                         double* counts) = 0;
+    };
+    static bool is_newton(const Function& f);
+    static NewtonPlan newton_plan(const Function& rootfinder);
+    /** Newton::solve for N instances; arg / res as Map::eval_gen.  Returns 0, or 1 when an instance failed and the
+        rootfinder has error_on_fail (Rootfinder::eval raises in that case, rootfinder.cpp:294-296); n_failed and the
+        launch counts are reported. */
+    static int newton_run(const NewtonPlan& P, casadi_int N, const double* const* arg, double* const* res, NewtonBackend& be,
+                          casadi_int* n_failed, casadi_int* n_singular, casadi_int launches[2]);
+
     /** Keep a mapped function that is itself a Map as ONE instance (its inner map is expanded into the tape) instead
         of flattening it to n*d device instances.  CudaMapSum needs this: a reduced input belongs to a whole
         instance of f_ and a reduced output is the sum of whole f_ outputs (mapsum.cpp:154-186).  Call before init. */
@@ -116,6 +158,8 @@ namespace casadi {
     // builder of libcasadi_cuda.so; the recorded program lives in builder_ (one compiled tape per memory)
     void* builder_;
     bool has_flag_;  // extra summed output: instances whose linear solver factorization failed
+    bool newton_;    // the leaf is a Newton rootfinder: evaluated by newton_run on device-resident state
+    NewtonPlan newton_plan_;
     void export_function();
     void lower_mx();
   };

@@ -220,6 +220,124 @@ static void check_close(const std::vector<std::vector<double>>& got, const std::
   CHECK(rel <= rtol, what + ": relative error " + str(rel));
 }
 
+// ---- SURVEY 8f-4, second half: the Newton rootfinder (casadi/solvers/newton.cpp) under a map.  Host-side check: the two
+// tapes of CudaMap::newton_plan are evaluated by the oracle over plain arrays, driven by the same CudaMap::newton_run
+// loop the device uses; expected = the reference's Newton::solve through rf.map(n, "serial"), bit for bit.
+struct OracleNewtonBackend : public CudaMap::NewtonBackend {
+  const CudaMap::NewtonPlan& P;
+  explicit OracleNewtonBackend(const CudaMap::NewtonPlan& p) : P(p) {}
+  double* alloc(casadi_int n) override { return new double[n]; }
+  void release(double* p) override { delete[] p; }
+  void upload(double* dst, const double* src, casadi_int n) override {
+    if (src) std::memcpy(dst, src, n * 8); else std::fill(dst, dst + n, 0.0);
+  }
+  void download(double* dst, const double* src, casadi_int n) override { std::memcpy(dst, src, n * 8); }
+  int launch(int which, casadi_int N, const std::vector<const double*>& arg, const std::vector<double*>& res, double* counts) override {
+    const CudaMap::Tape& t = P.tape[which];
+    std::vector<long long> ni(t.nnz_in.begin(), t.nnz_in.end()), no(t.nnz_out.begin(), t.nnz_out.end());
+    std::vector<double> cnt(N * CudaMap::NEWTON_COUNTS), w(t.sz_w + 1);
+    std::vector<double*> r(res);
+    r.back() = cnt.data();
+    int flag = oracle_map_eval(static_cast<long long>(t.op.size()), t.op.data(), t.i0.data(), t.i1.data(), t.i2.data(), t.d.data(),
+                               static_cast<long long>(ni.size()), ni.data(), static_cast<long long>(no.size()), no.data(), N,
+                               arg.data(), r.data(), w.data());
+    for (int k = 0; k < CudaMap::NEWTON_COUNTS; ++k) {
+      counts[k] = 0;
+      for (casadi_int i = 0; i < N; ++i) counts[k] += cnt[i * CudaMap::NEWTON_COUNTS + k];
+    }
+    return flag;
+  }
+};
+
+// the rootfinders of the checks: (0) x^2 - y, the reference's own mapped case (test/python/linearsolver.py:541-549);
+// (1) a 2 x 2 system with a parameter and an auxiliary output, exact-class; (2) atan(x) = y/4 from far away (the line
+// search must damp the step); (3) as (0) without line search and with too few iterations, failures ignored
+static Function newton_case(int which) {
+  if (which == 0 || which == 3) {
+    MX x = MX::sym("x"), y = MX::sym("y");
+    Function f("f", {x, y}, {x * x - y});
+    Dict opts = {{"linear_solver", "qr"}};
+    if (which == 3) { opts["line_search"] = false; opts["max_iter"] = 3; opts["error_on_fail"] = false; }
+    return rootfinder("finv" + str(which), "newton", f, opts);
+  } else if (which == 1) {
+    SX x = SX::sym("x", 2), p = SX::sym("p", 2);
+    SX g = vertcat(x(0) * x(0) + x(1) * x(1) - (3 + p(0)), x(0) - x(1) * (1 + p(1) / 4));
+    Function f("g2", {x, p}, {g, x(0) * x(1) + p(0)});
+    return rootfinder("rf2", "newton", f, Dict{{"max_iter", 60}});
+  }
+  SX x = SX::sym("x"), y = SX::sym("y");
+  Function f("fatan", {x, y}, {atan(x) - y / 4});
+  return rootfinder("rfatan", "newton", f, Dict{{"max_iter", 80}});
+}
+
+static std::vector<std::vector<double>> newton_inputs(int which, casadi_int n) {
+  std::vector<std::vector<double>> in(2);
+  std::mt19937_64 g(97 + which);
+  auto U = [&](double lo, double hi) { return lo + (hi - lo) * std::generate_canonical<double, 53>(g); };
+  if (which == 0 || which == 3) {
+    in[0].assign(n, 1.0);
+    for (casadi_int i = 0; i < n; ++i) in[1].push_back(n > 1 ? 10.0 * i / (n - 1) : 2.0);  // y = 0: a double root, ~20 iterations
+  } else if (which == 1) {
+    for (casadi_int i = 0; i < n; ++i) { in[0].push_back(U(0.5, 2.5)); in[0].push_back(U(0.5, 2.5)); in[1].push_back(U(-1, 1)); in[1].push_back(U(-1, 1)); }
+  } else {
+    for (casadi_int i = 0; i < n; ++i) { in[0].push_back(U(-4, 4)); in[1].push_back(U(-3, 3)); }
+  }
+  return in;
+}
+
+static void newton_lowering_checks() {
+  const casadi_int n = 200;
+  for (int which = 0; which < 4; ++which) {
+    Function rf = newton_case(which);
+    CHECK(CudaMap::is_newton(rf), rf.class_name());
+    Function ref = rf.map(n, "serial");
+    auto in = newton_inputs(which, n);
+    auto want = eval(ref, in);
+    CudaMap::NewtonPlan P = CudaMap::newton_plan(rf);
+    OracleNewtonBackend be(P);
+    std::vector<std::vector<double>> got(rf.n_out());
+    std::vector<const double*> arg(rf.n_in());
+    std::vector<double*> res(rf.n_out());
+    for (casadi_int j = 0; j < rf.n_in(); ++j) arg[j] = in[j].data();
+    for (casadi_int j = 0; j < rf.n_out(); ++j) { got[j].assign(rf.nnz_out(j) * n, -777.0); res[j] = got[j].data(); }
+    casadi_int n_failed = -1, n_singular = -1, launches[2] = {0, 0};
+    int flag = CudaMap::newton_run(P, n, arg.data(), res.data(), be, &n_failed, &n_singular, launches);
+    CHECK(flag == 0, "newton_run flag " + str(flag));
+    CHECK(n_singular == 0, "singular " + str(n_singular));
+    CHECK(which == 3 ? n_failed > 0 : n_failed == 0, "failed instances: " + str(n_failed));
+    check_bits(got, want, "Newton rootfinder case " + str(which));
+    printf("newton case %d: tapes %zu + %zu instructions, %lld direction + %lld line-search launches, %lld failed, x[last] = %.17g\n", which,
+           P.tape[0].op.size(), P.tape[1].op.size(), (long long)launches[0], (long long)launches[1], (long long)n_failed, want[0].back());
+  }
+}
+
+static void newton_gpu_checks() {
+  for (int which : {0, 1, 3}) {  // (case 2 calls atan: device libm, compared with a tolerance below)
+    for (casadi_int n : {200, 5000}) {
+      Function rf = newton_case(which);
+      Function ref = rf.map(n, "serial"), F = rf.map(n, "cuda");
+      CHECK(F.class_name() == "CudaMap", F.class_name());
+      auto in = newton_inputs(which, n);
+      check_bits(eval(F, in), eval(ref, in), "Newton rootfinder case " + str(which) + " under map(" + str(n) + ", cuda)");
+    }
+  }
+  {
+    Function rf = newton_case(2);
+    Function ref = rf.map(3000, "serial"), F = rf.map(3000, "cuda");
+    auto in = newton_inputs(2, 3000);
+    check_close(eval(F, in), eval(ref, in), 1e-9, "Newton rootfinder with atan under map(cuda)");
+  }
+  {  // too few iterations with error_on_fail (the default): the reference raises, so does the device map
+    MX x = MX::sym("x"), y = MX::sym("y");
+    Function rf = rootfinder("finv_fail", "newton", Function("f", {x, y}, {x * x - y}), Dict{{"max_iter", 2}});
+    Function F = rf.map(50, "cuda");
+    auto in = newton_inputs(0, 50);
+    bool threw = false;
+    try { eval(F, in); } catch (std::exception& e) { threw = std::string(e.what()).find("rootfinder process failed") != std::string::npos; }
+    CHECK(threw, "a failed rootfinder instance must raise like Rootfinder::eval");
+  }
+}
+
 static void integrator_gpu_checks() {
   for (casadi_int n : {3, 1000, 70000}) {
     // exact-class dynamics: the device evaluation has the bits of Integrator::eval
@@ -532,7 +650,8 @@ int main(int argc, char** argv) {
   try {
     host_side_checks();
     integrator_lowering_checks();
-    if (no_gpu) no_gpu_checks(); else { gpu_checks(); kkt_checks(); integrator_gpu_checks(); }
+    newton_lowering_checks();
+    if (no_gpu) no_gpu_checks(); else { gpu_checks(); kkt_checks(); integrator_gpu_checks(); newton_gpu_checks(); }
   } catch (std::exception& e) {
     printf("FAIL: unexpected exception: %s\n", e.what());
     return 1;
