@@ -845,10 +845,10 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
   const size_t n_in = t->nnz_in.size(), n_out = t->nnz_out.size();
   HostPipe& hp = t->pipe;
   cudaStream_t s_h2d = hp.s[0], s_cmp = hp.s[1], s_d2h = hp.s[2];
-  // chunk size: a multiple of kReduceBlock; ~8 chunks per call, between 64Ki and 1Mi instances
+  // chunk size: a multiple of kReduceBlock; ~8 chunks per call, between 64Ki and 512Ki instances
   long long C = (N + 7) / 8;
   if (const char* p = getenv("CCU_HOST_CHUNK")) C = atoll(p);
-  else C = std::max<long long>(1 << 16, std::min<long long>(1 << 20, C));
+  else C = std::max<long long>(1 << 16, std::min<long long>(1 << 19, C));  // (quad_ms, 4e6 instances: 256-512 Ki chunks +4 % over 1 Mi)
   C = std::max<long long>(ccu::kReduceBlock, (C + ccu::kReduceBlock - 1) / ccu::kReduceBlock * ccu::kReduceBlock);
   const long long nchunks = N > 0 ? (N + C - 1) / C : 0;
   const long long nblocks = (N_glob + ccu::kReduceBlock - 1) / ccu::kReduceBlock;

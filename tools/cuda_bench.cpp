@@ -136,6 +136,30 @@ int main(int argc, char** argv) {
       const double dt = now() - t0;
       if (r >= warm) secs.push_back(dt);
     }
+    // optional sweep of the host pipeline's chunk size on the same maps (CUDA_BENCH_CHUNK_SWEEP="65536,131072,..."):
+    // the library reads CCU_HOST_CHUNK at every call, so no map has to be rebuilt
+    if (const char* sweep = getenv("CUDA_BENCH_CHUNK_SWEEP")) {
+      std::string list = sweep;
+      size_t pos = 0;
+      while (pos < list.size()) {
+        size_t c = list.find(',', pos);
+        if (c == std::string::npos) c = list.size();
+        const std::string item = list.substr(pos, c - pos);
+        pos = c + 1;
+        if (item.empty()) continue;
+        setenv("CCU_HOST_CHUNK", item.c_str(), 1);
+        std::vector<double> ss;
+        for (int r = 0; r < reps + 1; ++r) {
+          const double t0 = now();
+          for (Job& j : jobs) casadi_assert(j.F(j.arg.data(), j.res.data(), j.iw.data(), j.w.data(), 0) == 0, "evaluation failed");
+          if (r >= 1) ss.push_back(now() - t0);
+        }
+        std::sort(ss.begin(), ss.end());
+        fprintf(stderr, "chunk_sweep %s %s: chunk %s -> %.6f s, %.4g evals/s\n", wl.c_str(), memkind.c_str(), item.c_str(),
+                ss[ss.size() / 2], static_cast<double>(n) / ss[ss.size() / 2]);
+      }
+      unsetenv("CCU_HOST_CHUNK");
+    }
     // parity of the timed run's results: first / last instances against the reference's serial evaluation of f
     double worst = 0;
     for (Job& j : jobs) {
