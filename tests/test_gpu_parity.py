@@ -15,7 +15,9 @@ pytestmark = pytest.mark.gpu
 MODES = ["interp", "jit"]  # both product paths: the interpreter kernel and the NVRTC-specialised kernels
 
 ULP_TOL = 2          # transcendentals: |device - reference libm| <= 2 ulp
-COMPOSITE_RTOL = 1e-11  # whole tapes that chain transcendentals into arithmetic (ulp errors propagate)
+# whole tapes that chain transcendentals into arithmetic (ulp errors propagate).  Observed on a B200 against the reference's
+# goldens (glibc): worst |got - want| / max(|want|, 1) = 3.7e-16 over all composite tapes (profiles/r2_composite_ulp.txt)
+COMPOSITE_RTOL = 1e-13
 
 
 def opcover_output_ops():
@@ -104,11 +106,18 @@ def test_exactified_tapes_bit_exact_vs_oracle(name, mode):
 def test_composite_tapes_vs_reference(name, mode):
     tape, case = load_tape(name), load_case(name)
     outs = CudaMap(tape, case["N"], mode=mode)(case["in"])
+    worst_rel, worst_ulp = 0.0, 0.0
     for j, (g, w) in enumerate(zip(outs, case["out"])):
         scale = np.maximum(np.abs(w), 1.0)
         err = np.abs(g - w) / scale
         assert np.all(np.isfinite(g) == np.isfinite(w))
         assert np.nanmax(err, initial=0.0) <= COMPOSITE_RTOL, "%s out%d: rel err %g" % (name, j, np.nanmax(err))
+        worst_rel = max(worst_rel, float(np.nanmax(err, initial=0.0)))
+        fin = np.isfinite(w) & (w != 0)
+        if fin.any():
+            worst_ulp = max(worst_ulp, float(np.max(np.abs(g[fin] - w[fin]) / np.spacing(np.abs(w[fin])))))
+    # the observed distance to the reference (glibc transcendentals) -- recorded in DESIGN section 5 (run with -s)
+    print("COMPOSITE %s %s: worst rel err %.3g, worst distance %.1f ulp of the reference value" % (name, mode, worst_rel, worst_ulp))
 
 
 @pytest.mark.parametrize("name,plans", [("cartpole", [(128, 1, 0), (64, 2, 0), (256, 4, 0), (128, 1, 8), (32, 2, 5)]),
