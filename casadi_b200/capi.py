@@ -98,6 +98,9 @@ SYMBOLS = {
     "ccu_free": (ctypes.c_int, [c_vp]),
     "ccu_malloc_host": (c_vp, [c_ll]),
     "ccu_free_host": (ctypes.c_int, [c_vp]),
+    "ccu_host_register": (ctypes.c_int, [c_vp, c_ll]),
+    "ccu_host_unregister": (ctypes.c_int, [c_vp]),
+    "ccu_host_registered_count": (ctypes.c_int, []),
     "ccu_memcpy_h2d": (ctypes.c_int, [c_vp, c_vp, c_ll, c_vp]),
     "ccu_memcpy_d2h": (ctypes.c_int, [c_vp, c_vp, c_ll, c_vp]),
     "ccu_stream_sync": (ctypes.c_int, [c_vp]),

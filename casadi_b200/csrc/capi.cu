@@ -12,7 +12,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstdint>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -172,6 +174,74 @@ bool host_ptr_is_pinned(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// Page-locking the caller's buffers IN PLACE (cudaHostRegister), so that the DMA engines read and write them directly and
+// the pinned staging (one extra read + write of every byte through the host memory system) drops out of the host path.
+// Strictly opt-in -- ccu_host_register() or CCU_HOST_REGISTER=1 -- because a registration outlives a free() of the
+// buffer: a caller that pins must keep the buffer alive until ccu_host_unregister() / the destruction of the tape that
+// registered it (the reference's buffer API, Function::operator()(arg,res,iw,w,mem), is called with long-lived
+// buffers; its DM API allocates fresh results per call and should not pin).
+class HostRegistry {
+ public:
+  static HostRegistry& get() { static HostRegistry* r = new HostRegistry; return *r; }
+  // 0: [p, p+bytes) is page-locked on return (by us, now or earlier, or by the caller); 1: it is not (stage it)
+  int pin(const void* p, size_t bytes, const void* owner) {
+    if (!p || bytes == 0) return 1;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = map_.upper_bound(a);
+    if (it != map_.begin()) {
+      --it;
+      if (it->first + it->second.bytes >= a + bytes) return 0;  // covered by an earlier registration
+      if (it->first == a) {  // the same buffer grew: register it again in full
+        cudaHostUnregister(reinterpret_cast<void*>(it->first));
+        cudaGetLastError();
+        map_.erase(it);
+      }
+    }
+    if (host_ptr_is_pinned(p) && host_ptr_is_pinned(static_cast<const char*>(p) + bytes - 1)) return 0;  // the caller's own
+    const cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return 1; }  // (overlaps a foreign registration, locked-memory limit, ...)
+    map_[a] = Entry{bytes, owner};
+    return 0;
+  }
+  int unpin(const void* p) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = map_.find(reinterpret_cast<uintptr_t>(p));
+    if (it == map_.end()) return 1;
+    const cudaError_t e = cudaHostUnregister(const_cast<void*>(p));
+    cudaGetLastError();
+    map_.erase(it);
+    return e == cudaSuccess ? 0 : 1;
+  }
+  void release_owner(const void* owner) {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto it = map_.begin(); it != map_.end();) {
+      if (it->second.owner == owner) {
+        cudaHostUnregister(reinterpret_cast<void*>(it->first));
+        cudaGetLastError();
+        it = map_.erase(it);
+      } else {
+        ++it;
+      }
+    }
+  }
+  size_t count() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return map_.size();
+  }
+
+ private:
+  struct Entry { size_t bytes; const void* owner; };
+  std::mutex mu_;
+  std::map<uintptr_t, Entry> map_;
+};
+
+// CCU_HOST_REGISTER=1: page-lock every mapped caller buffer of at least 1 MiB the first time an evaluation sees it
+bool host_register_auto() {
+  const char* e = getenv("CCU_HOST_REGISTER");
+  return e && atoi(e) != 0;
 }
 
 // staging of the host-pointer path (eval_host_impl): [slot] buffering
@@ -516,6 +586,7 @@ ccu_tape* ccu_tape_create(ccu_int n_instr, const int* op, const int* i0, const i
 
 void ccu_tape_destroy(ccu_tape* t) {
   if (!t) return;
+  HostRegistry::get().release_owner(t);
   if (t->device >= 0) {
     cudaSetDevice(t->device);
     if (t->d_prog) cudaFree(t->d_prog);
@@ -1054,6 +1125,23 @@ static int eval_host_chunks(ccu_tape* t, ccu_int N, const double* const* arg, do
   return 0;
 }
 
+// Opt-in page-locking of the whole-batch caller buffers (HostRegistry) before the chunked pipeline looks at them: a
+// buffer that is page-locked afterwards is copied by the DMA engines directly (host_ptr_is_pinned in eval_host_chunks).
+static void register_caller_buffers(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res,
+                                    const int* reduce_in, const int* reduce_out) {
+  if (!host_register_auto() || N <= 0) return;
+  const size_t kMin = size_t(1) << 20;
+  HostRegistry& reg = HostRegistry::get();
+  for (size_t j = 0; j < t->nnz_in.size(); ++j) {
+    const size_t bytes = static_cast<size_t>(N) * t->nnz_in[j] * 8;
+    if (arg[j] && bytes >= kMin && !(reduce_in && reduce_in[j])) reg.pin(arg[j], bytes, t);
+  }
+  for (size_t j = 0; j < t->nnz_out.size(); ++j) {
+    const size_t bytes = static_cast<size_t>(N) * t->nnz_out[j] * 8;
+    if (res[j] && bytes >= kMin && !(reduce_out && reduce_out[j])) reg.pin(res[j], bytes, t);
+  }
+}
+
 static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, double* const* res,
                           const int* reduce_in, const int* reduce_out, long long g_off = 0, long long N_glob = -1,
                           bool finish_reduce = true, const int* in_groups = nullptr, const int* out_groups = nullptr) {
@@ -1076,6 +1164,7 @@ static int eval_host_impl(ccu_tape* t, ccu_int N, const double* const* arg, doub
     hp.bcast.resize(n_in);
     hp.ready = true;
   }
+  if (g_off == 0 && N_glob == N) register_caller_buffers(t, N, arg, res, reduce_in, reduce_out);  // (a shard: done by the caller)
   t->st_h2d_ms = t->st_kernel_ms = t->st_d2h_ms = t->st_stage_ms = t->st_wall_ms = t->st_staged_bytes = 0;
   for (int b = 0; b < HostPipe::kSlots; ++b) hp.tev_used[b] = false;
   const auto t0 = std::chrono::steady_clock::now();
@@ -1258,6 +1347,7 @@ int ccu_multi_eval_host_grouped(ccu_multi* m, ccu_int N, const double* const* ar
     const long long b0 = g * per + std::min<long long>(g, extra);
     off[g] = std::min<long long>(b0 * ccu::kReduceBlock, N);
   }
+  if (arg && res) register_caller_buffers(t0, N, arg, res, reduce_in, reduce_out);
   bool any_red = false;
   for (size_t j = 0; j < n_out; ++j) any_red = any_red || (reduce_out && reduce_out[j] && res[j] && t0->nnz_out[j] > 0);
   std::vector<int> rcs(G, 0);
@@ -1526,6 +1616,16 @@ void* ccu_malloc_host(ccu_int bytes) {
   return p;
 }
 int ccu_free_host(void* p) { CCU_CUDA(cudaFreeHost(p)); return 0; }
+int ccu_host_register(const void* p, ccu_int bytes) {
+  if (!p || bytes <= 0) return fail("ccu_host_register: null buffer or no bytes");
+  if (HostRegistry::get().pin(p, static_cast<size_t>(bytes), nullptr)) return fail("ccu_host_register: cudaHostRegister of %lld bytes at %p failed", bytes, p);
+  return 0;
+}
+int ccu_host_unregister(const void* p) {
+  if (HostRegistry::get().unpin(p)) return fail("ccu_host_unregister: %p was not registered by ccu_host_register / CCU_HOST_REGISTER", p);
+  return 0;
+}
+int ccu_host_registered_count(void) { return static_cast<int>(HostRegistry::get().count()); }
 int ccu_memcpy_h2d(void* dst, const void* src, ccu_int bytes, void* stream) {
   CCU_CUDA(cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
   return 0;

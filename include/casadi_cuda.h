@@ -356,6 +356,17 @@ CCU_EXPORT void* ccu_malloc(ccu_int bytes);
 CCU_EXPORT int ccu_free(void* p);
 CCU_EXPORT void* ccu_malloc_host(ccu_int bytes); /* pinned */
 CCU_EXPORT int ccu_free_host(void* p);
+/* Page-lock a caller's buffer IN PLACE (cudaHostRegister, portable across devices): ccu_map_eval_host and friends then
+ * let the DMA engines read / write it directly instead of copying every byte through the library's pinned staging
+ * (quadrotor step end to end: +45 % when the buffers are long-lived).  The buffer must stay allocated until
+ * ccu_host_unregister; a buffer that is page-locked already (cudaHostAlloc, the caller's own cudaHostRegister) needs
+ * nothing.  CCU_HOST_REGISTER=1 in the environment does the same automatically for every mapped buffer of >= 1 MiB the
+ * first time an evaluation sees it, and un-registers when the tape is destroyed -- meant for the reference's buffer API
+ * (Function::operator()(arg,res,iw,w,mem), function.hpp) called repeatedly with the same buffers, NOT for callers that
+ * free and re-allocate buffers between calls.  ccu_host_registered_count: registrations currently held. */
+CCU_EXPORT int ccu_host_register(const void* p, ccu_int bytes);
+CCU_EXPORT int ccu_host_unregister(const void* p);
+CCU_EXPORT int ccu_host_registered_count(void);
 CCU_EXPORT int ccu_memcpy_h2d(void* dst, const void* src, ccu_int bytes, void* stream);
 CCU_EXPORT int ccu_memcpy_d2h(void* dst, const void* src, ccu_int bytes, void* stream);
 CCU_EXPORT int ccu_stream_sync(void* stream);

@@ -460,3 +460,44 @@ def test_host_path_pageable_staging_and_phase_stats(monkeypatch):
         assert_bit_equal(a, b, "pinned staging vs driver-staged copies, out%d" % j)
     got = staged[0].reshape(N, -1)
     assert_bit_equal(got[P * (reps - 2):P * (reps - 1)].ravel(), got[:P].ravel(), "a late period vs period 0")
+
+
+def test_host_path_page_locked_caller_buffers(monkeypatch):
+    """ccu_host_register / CCU_HOST_REGISTER=1 page-lock the caller's own buffers in place: the host path then copies
+    them by DMA directly (nothing is staged), with the bits of the staged evaluation; the tape un-registers what the
+    automatic mode registered when it is destroyed."""
+    L = capi.lib()
+    tape, case = load_tape("quad"), load_case("quad")
+    P, reps = case["N"], 1500
+    N = P * reps - 13
+    ins = [np.tile(a, reps)[:N * int(n)].copy() for a, n in zip(case["in"], tape["nnz_in"])]
+    t = CudaTape(tape, mode="jit")
+    monkeypatch.setenv("CCU_HOST_CHUNK", "16384")
+    staged = CudaMap(t, N)(ins)
+    assert t.last_eval_stats()["staged_bytes"] == 8 * N * (sum(t.nnz_in) + sum(t.nnz_out))
+    base = L.ccu_host_registered_count()
+    # explicit registration of the inputs: only the results (fresh numpy buffers) are still staged
+    for a in ins:
+        capi.check(L.ccu_host_register(a.ctypes.data, a.nbytes))
+    assert L.ccu_host_registered_count() == base + len(ins)
+    mixed = CudaMap(t, N)(ins)
+    assert t.last_eval_stats()["staged_bytes"] == 8 * N * sum(t.nnz_out)
+    for a in ins:
+        capi.check(L.ccu_host_unregister(a.ctypes.data))
+    assert L.ccu_host_unregister(ins[0].ctypes.data) != 0  # not registered any more: refused
+    assert L.ccu_host_registered_count() == base
+    # automatic registration of caller-owned inputs AND results (raw C ABI call: the buffers outlive the tape)
+    outs = [np.full(N * int(n), np.nan) for n in tape["nnz_out"]]
+    monkeypatch.setenv("CCU_HOST_REGISTER", "1")
+    t2 = CudaTape(tape, mode="jit")
+    a_ptr, r_ptr = capi.ptr_array([a.ctypes.data for a in ins]), capi.ptr_array([o.ctypes.data for o in outs])
+    for _ in range(2):
+        capi.check(L.ccu_map_eval_host(t2.handle, N, a_ptr, r_ptr))
+        assert t2.last_eval_stats()["staged_bytes"] == 0
+    assert L.ccu_host_registered_count() == base + len(ins) + len(outs)
+    t2.close()
+    assert L.ccu_host_registered_count() == base
+    monkeypatch.delenv("CCU_HOST_REGISTER")
+    for j, (a, b, c) in enumerate(zip(staged, mixed, outs)):
+        assert_bit_equal(a, b, "staged vs registered inputs, out%d" % j)
+        assert_bit_equal(a, c, "staged vs automatically registered buffers, out%d" % j)

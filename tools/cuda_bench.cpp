@@ -2,10 +2,11 @@
 // reference's own public C++ API -- Function::map -> Map::create -> CudaMap (casadi_b200/host/cuda_map.cpp), then
 // F(arg, res, iw, w, 0) -> FunctionInternal::eval_gen -> CudaMap::eval -- inside the relinked reference library
 // (tests/integration/build_integration.py), with the buffers a CasADi caller owns: ordinary pageable std::vector
-// storage (default) or pinned memory ("pinned").  Host<->device copies are inside the timed region; construction
+// storage (default), the same storage page-locked in place by the library ("registered", CCU_HOST_REGISTER=1) or pinned
+// memory ("pinned").  Host<->device copies are inside the timed region; construction
 // (Map sparsity repmat + tape export + specialisation) is timed separately.
 //
-// usage: cuda_bench <workload> <n> <reps> <warmup> [pageable|pinned] [reduce]
+// usage: cuda_bench <workload> <n> <reps> <warmup> [pageable|pinned|registered] [reduce]
 //   workload: cartpole | quad | quad_jac | quad_ms (= quad then quad_jac) | rocket_hess | mc | kkt_ldl | kkt_qr
 //   reduce:   map with every output summed over the instances (Function::map(name, "cuda", n, {}, all outputs)):
 //             BASELINE config 4 (mapaccum rollout with reduce_out)
@@ -60,7 +61,7 @@ double now() { return std::chrono::duration<double>(std::chrono::steady_clock::n
 
 int main(int argc, char** argv) {
   if (argc < 5) {
-    fprintf(stderr, "usage: cuda_bench <workload> <n> <reps> <warmup> [pageable|pinned] [reduce]\n");
+    fprintf(stderr, "usage: cuda_bench <workload> <n> <reps> <warmup> [pageable|pinned|registered] [reduce]\n");
     return 2;
   }
   const std::string wl = argv[1];
@@ -80,6 +81,10 @@ int main(int argc, char** argv) {
   try {
     HostAlloc A;
     A.pinned = memkind == "pinned";
+    casadi_assert(memkind == "pageable" || memkind == "pinned" || memkind == "registered", "buffers: pageable | pinned | registered");
+    // "registered": the same malloc buffers, page-locked in place by the library the first time it sees them (the warm-up
+    // call), include/casadi_cuda.h: ccu_host_register.  The maps are destroyed (and un-register) before A frees the buffers.
+    if (memkind == "registered") setenv("CCU_HOST_REGISTER", "1", 1);
     if (A.pinned) {
       const char* lib = getenv("CASADI_CUDA_LIB");
       void* h = dlopen(lib ? lib : "libcasadi_cuda.so", RTLD_NOW | RTLD_GLOBAL);
@@ -201,11 +206,17 @@ int main(int argc, char** argv) {
       }
     }
     stats += "}";
+    int registered = 0;  // buffers the library holds page-locked ("registered" mode; 0 when the registration was refused)
+    {
+      const char* lib = getenv("CASADI_CUDA_LIB");
+      void* h = dlopen(lib ? lib : "libcasadi_cuda.so", RTLD_NOW | RTLD_GLOBAL);
+      if (h) if (auto cnt = reinterpret_cast<int (*)()>(dlsym(h, "ccu_host_registered_count"))) registered = cnt();
+    }
     printf("{\"workload\": \"%s\", \"n\": %lld, \"memory\": \"%s\", \"reduce\": %s, \"reps\": %d, \"secs_median\": %.6f, "
            "\"secs_best\": %.6f, \"secs_total\": %.6f, \"evals_per_s\": %.6g, \"construct_s\": %.3f, "
-           "\"h2d_bytes_per_step\": %lld, \"d2h_bytes_per_step\": %lld, \"parity_rel_err\": %.3g, \"fstats\": %s}\n",
+           "\"h2d_bytes_per_step\": %lld, \"d2h_bytes_per_step\": %lld, \"parity_rel_err\": %.3g, \"registered_buffers\": %d, \"fstats\": %s}\n",
            wl.c_str(), n, memkind.c_str(), reduce ? "true" : "false", reps, secs[secs.size() / 2], secs.front(), total,
-           static_cast<double>(n) * reps / total, construct, h2d, d2h, worst, stats.c_str());
+           static_cast<double>(n) * reps / total, construct, h2d, d2h, worst, registered, stats.c_str());
     fflush(stdout);
   } catch (std::exception& e) {
     fprintf(stderr, "cuda_bench: %s\n", e.what());
