@@ -4,6 +4,7 @@
 #include "cuda_map.hpp"
 #include "integrator_impl.hpp"
 #include "linsol.hpp"
+#include "mapsum.hpp"
 #include "multiplication.hpp"
 #include "rootfinder_impl.hpp"
 #include <casadi/solvers/newton.hpp>  // option members of the Newton plugin class (layout only; nothing is linked)
@@ -244,11 +245,17 @@ namespace casadi {
             w[out.at(0)] = r;
           } else if (o == OP_MTIMES) {
             // Multiplication::eval_kernel = casadi_mtimes (multiplication.cpp:64-67); the dense variants call BLAS
-            casadi_assert(dynamic_cast<const DenseMultiplication*>(x.get()) == nullptr
-                          && dynamic_cast<const PseudoDenseMultiplication*>(x.get()) == nullptr
-                          && dynamic_cast<const DenseSparseMultiplication*>(x.get()) == nullptr,
-                          "Map 'cuda': dense matrix products (" + x.class_name() + ") are not supported on the "
-                          "device (only the sparse casadi_mtimes kernel is)");
+            if (dynamic_cast<const DenseMultiplication*>(x.get()) != nullptr
+                || dynamic_cast<const PseudoDenseMultiplication*>(x.get()) != nullptr
+                || dynamic_cast<const DenseSparseMultiplication*>(x.get()) != nullptr) {
+              // the dense variants run casadi_mtimes_dense / casadi_mtimes_dense_sparse for T = double and T = SXElem alike
+              // (multiplication.cpp:172-258) as long as the node's BLAS backend is "reference" (Blas::mtimes, blas.cpp:201-210);
+              // a BLAS plugin sums in its own order and has no device counterpart
+              casadi_assert(blas_is_reference(x), "Map 'cuda': dense matrix products through a BLAS plugin ("
+                            + x.class_name() + ") are not supported on the device (only the reference loops are)");
+              node_sx(f, x, in, out, w);
+              continue;
+            }
             Vals z = W(in.at(0));
             const Vals &xx = W(in.at(1)), &yy = W(in.at(2));
             std::vector<ccu_int> spx = pattern(x.dep(1).sparsity()), spy = pattern(x.dep(2).sparsity()),
@@ -295,7 +302,10 @@ namespace casadi {
             w[out.at(0)] = W(in.at(0));
           } else if (o == OP_GETNONZEROS) {
             Dict inf = x.info();
-            casadi_assert(inf.find("nz") != inf.end(), "Map 'cuda': " + x.class_name() + " (sliced GetNonzeros) is not supported");
+            if (inf.find("nz") == inf.end()) {  // the slice forms (GetNonzerosSlice / Slice2, getnonzeros.cpp)
+              node_sx(f, x, in, out, w);
+              continue;
+            }
             std::vector<casadi_int> nz = inf.at("nz");
             const Vals& v = W(in.at(0));
             Vals r(nz.size());
@@ -329,11 +339,82 @@ namespace casadi {
             Vals r(a.size());
             for (size_t e = 0; e < a.size(); ++e) r[e] = op(static_cast<int>(o), a[e]);
             w[out.at(0)] = r;
+          } else if (o == OP_TRANSPOSE || o == OP_PROJECT || o == OP_DOT || o == OP_BILIN || o == OP_RANK1 || o == OP_NORMF
+                     || o == OP_SETNONZEROS || o == OP_ADDNONZEROS || o == OP_MMIN || o == OP_MMAX || o == OP_SPARSITY_CAST
+                     || o == OP_LIFT) {
+            node_sx(f, x, in, out, w);
           } else {
             casadi_error("Map 'cuda': MX operation '" + x.class_name() + "' (op " + str(o) + ") in function '" + f.name()
                          + "' has no device lowering");
           }
         }
+      }
+
+      // true when a Multiplication node multiplies with the reference loops (blas_shorthand_ == 0, multiplication.hpp:207)
+      static bool blas_is_reference(const MX& x) {
+        struct Peek : public Multiplication { using Multiplication::blas_shorthand_; };
+        casadi_int Multiplication::* member = &Peek::blas_shorthand_;
+        const Multiplication* m = dynamic_cast<const Multiplication*>(x.get());
+        return m != nullptr && m->*member == 0;
+      }
+
+      // A node whose numeric eval and eval_sx instantiate ONE template (eval_gen<T>, casadi_*<T1> of the runtime): the
+      // reference's own symbolic evaluation of the node on fresh symbols -- exactly what Function::expand() runs for it
+      // (MXFunction::eval_sx, mx_function.cpp:1229-1278) -- wrapped into an SX function and inlined like any other.
+      // Pure data movement (transpose, project, get/set nonzeros) records nothing.  As in an expansion, SX drops the
+      // additions of the constant zeros a node starts its accumulators from (0 + a*b is a*b): the sign of a zero result
+      // may differ from the numeric eval, nothing else.
+      void node_sx(const Function& f, const MX& x, const std::vector<casadi_int>& in, const std::vector<casadi_int>& out,
+                   std::map<casadi_int, Vals>& w) {
+        const casadi_int nd = x.n_dep(), no = static_cast<casadi_int>(out.size());
+        std::vector<SX> sa(nd), so(no);
+        std::vector<const SXElem*> argp(std::max<size_t>(x->sz_arg(), nd) + 1, nullptr);
+        std::vector<SXElem*> resp(std::max<size_t>(x->sz_res(), no) + 1, nullptr);
+        std::vector<SX> fin, fout;
+        std::vector<const Vals*> a;
+        for (casadi_int d = 0; d < nd; ++d) {
+          if (in.at(d) < 0) continue;
+          sa[d] = SX::sym("a" + str(d), x.dep(d).sparsity());
+          argp[d] = sa[d].ptr();
+          fin.push_back(sa[d]);
+          auto it = w.find(in[d]);
+          casadi_assert(it != w.end(), "Map 'cuda': MX work element read before it is written");
+          casadi_assert(static_cast<casadi_int>(it->second.size()) == x.dep(d).nnz(), "Map 'cuda': operand of " + x.class_name()
+                        + " has " + str(it->second.size()) + " nonzeros, expected " + str(x.dep(d).nnz()));
+          a.push_back(&it->second);
+        }
+        for (casadi_int k = 0; k < no; ++k) {
+          if (out[k] < 0) continue;
+          so[k] = SX::zeros(x->sparsity(k));
+          resp[k] = so[k].ptr();
+        }
+        std::vector<casadi_int> iw(x->sz_iw() + 1);
+        std::vector<SXElem> ww(x->sz_w() + 1);
+        int flag = 1;
+        std::string why;
+        try {
+          flag = x->eval_sx(argp.data(), resp.data(), iw.data(), ww.data());
+        } catch (std::exception& e) {
+          why = e.what();
+        }
+        casadi_assert(flag == 0, "Map 'cuda': MX operation '" + x.class_name() + "' in function '" + f.name()
+                      + "' has no device lowering (its symbolic evaluation failed" + (why.empty() ? "" : ": " + why) + ")");
+        std::vector<Vals> r;
+        std::vector<casadi_int> which;
+        for (casadi_int k = 0; k < no; ++k) {
+          if (out[k] < 0) continue;
+          fout.push_back(so[k]);
+          which.push_back(k);
+        }
+        r.resize(which.size());
+        std::vector<Vals*> rp(which.size());
+        for (size_t q = 0; q < which.size(); ++q) {
+          r[q].assign(fout[q].nnz(), cst(0.));
+          rp[q] = &r[q];
+        }
+        Function g("node_" + str(x.op()), fin, fout);
+        call_sx(g, a, rp);
+        for (size_t q = 0; q < which.size(); ++q) w[out[which[q]]] = r[q];
       }
 
       // A fixed-step integrator with an explicit step function (the "rk" plugin, runge_kutta.cpp:68-135): replays
@@ -417,6 +498,43 @@ namespace casadi {
         }
       }
 
+      // n evaluations of g over consecutive blocks of the operands (Map / MapSum); reduce_in: one shared block,
+      // reduce_out: zero, then += the instance's result in index order
+      void call_repeated(const Function& g, casadi_int n, const std::vector<bool>& reduce_in, const std::vector<bool>& reduce_out,
+                         const std::vector<const Vals*>& arg, std::vector<Vals*>& res) {
+        const casadi_int n_in = g.n_in(), n_out = g.n_out();
+        for (casadi_int j = 0; j < n_out; ++j)
+          if (res.at(j) && reduce_out.at(j)) res[j]->assign(g.nnz_out(j), cst(0.));
+        for (casadi_int i = 0; i < n; ++i) {
+          std::vector<Vals> a(n_in), r(n_out);
+          std::vector<const Vals*> ap(n_in, nullptr);
+          std::vector<Vals*> rp(n_out, nullptr);
+          for (casadi_int j = 0; j < n_in; ++j) {
+            if (!arg.at(j)) continue;
+            const casadi_int nz = g.nnz_in(j), off = reduce_in.at(j) ? 0 : i * nz;
+            casadi_assert(static_cast<casadi_int>(arg[j]->size()) >= off + nz, "Map 'cuda': operand " + str(j) + " of the embedded map '"
+                          + g.name() + "' is too short");
+            a[j].assign(arg[j]->begin() + off, arg[j]->begin() + off + nz);
+            ap[j] = &a[j];
+          }
+          for (casadi_int j = 0; j < n_out; ++j) {
+            if (!res.at(j)) continue;
+            r[j].assign(g.nnz_out(j), cst(0.));
+            rp[j] = &r[j];
+          }
+          call(g, ap, rp);
+          for (casadi_int j = 0; j < n_out; ++j) {
+            if (!res[j]) continue;
+            const casadi_int nz = g.nnz_out(j);
+            if (reduce_out.at(j)) {
+              for (casadi_int e = 0; e < nz; ++e) res[j]->at(e) = op(OP_ADD, res[j]->at(e), r[j][e]);
+            } else {
+              for (casadi_int e = 0; e < nz; ++e) res[j]->at(i * nz + e) = r[j][e];
+            }
+          }
+        }
+      }
+
       void call(const Function& f, const std::vector<const Vals*>& arg, std::vector<Vals*>& res) {
         if (f.is_a("SXFunction")) {
           call_sx(f, arg, res);
@@ -424,6 +542,21 @@ namespace casadi {
           call_mx(f, arg, res);
         } else if (auto* I = dynamic_cast<const FixedStepIntegrator*>(f.get())) {
           call_fixed_step(f, I, arg, res);
+        } else if (f.is_a("Map", true)) {
+          // a map embedded in the function (g.map(k) called from MX; any parallelization evaluates like "serial"):
+          // Map::eval_gen (map.cpp:141-157), instance i reads arg[j] + i*nnz_in(j) and writes res[j] + i*nnz_out(j)
+          Dict inf = f.info();
+          call_repeated(inf.at("f").to_function(), inf.at("n").to_int(), std::vector<bool>(f.n_in(), false),
+                        std::vector<bool>(f.n_out(), false), arg, res);
+        } else if (auto* ms = dynamic_cast<const MapSum*>(f.get())) {
+          // MapSum::eval_gen (mapsum.cpp:154-186): reduced inputs are shared, reduced outputs are cleared and then
+          // accumulated instance by instance, in index order (casadi_add: y += x)
+          struct Peek : public MapSum { using MapSum::f_; using MapSum::n_; using MapSum::reduce_in_; using MapSum::reduce_out_; };
+          Function MapSum::* pf = &Peek::f_;
+          casadi_int MapSum::* pn = &Peek::n_;
+          std::vector<bool> MapSum::* pri = &Peek::reduce_in_;
+          std::vector<bool> MapSum::* pro = &Peek::reduce_out_;
+          call_repeated(ms->*pf, ms->*pn, ms->*pri, ms->*pro, arg, res);
         } else {
           casadi_error("Map 'cuda': embedded function '" + f.name() + "' of class " + f.class_name()
                        + " has no device lowering");

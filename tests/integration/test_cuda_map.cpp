@@ -114,6 +114,141 @@ static void host_side_checks() {
   }
 }
 
+// ---- the MX vocabulary around a Linsol call (widened): a function that holds solve(K, b, "ldl") cannot be
+// expanded, so CudaMap lowers it node by node; every node class below must give the bits of the reference's own numeric
+// evaluation (f.map(n, "serial")).  The oracle evaluates the lowered tape on the host.
+static std::vector<std::vector<double>> eval_tape(const CudaMap::Tape& t, casadi_int n, const std::vector<std::vector<double>>& in);
+static void check_bits(const std::vector<std::vector<double>>& got, const std::vector<std::vector<double>>& want, const std::string& what);
+static std::vector<std::vector<double>> kkt_like_inputs(const Function& F, casadi_int n, unsigned seed) {
+  // input 0: a symmetric banded matrix (diagonal dominant so that LDL is well conditioned), the rest: U(-1, 1)
+  std::mt19937_64 g(seed);
+  std::vector<std::vector<double>> in(F.n_in());
+  for (casadi_int j = 0; j < F.n_in(); ++j) {
+    in[j].resize(F.nnz_in(j));
+    for (auto& v : in[j]) v = -1 + 2 * std::generate_canonical<double, 53>(g);
+  }
+  Sparsity sp = Sparsity::banded(6, 1);
+  const casadi_int nnz = sp.nnz();
+  std::vector<casadi_int> row = sp.get_row(), col = sp.get_col();
+  for (casadi_int i = 0; i < n; ++i)
+    for (casadi_int k = 0; k < nnz; ++k) {
+      double& v = in[0][i * nnz + k];
+      if (row[k] == col[k]) v = 4 + v;
+      else v = 0.25 * (1 + static_cast<double>((row[k] + col[k] + i) % 3));  // symmetric: depends on row + col only
+    }
+  return in;
+}
+
+static void mx_vocabulary_checks() {
+  const casadi_int n = 16;
+  Sparsity sp = Sparsity::banded(6, 1);
+  MX K = MX::sym("K", sp), b = MX::sym("b", 6), M = MX::sym("M", 3, 6), al = MX::sym("al");
+  MX x = solve(K, b, "ldl");
+  auto check = [&](const std::string& what, const std::vector<MX>& in, const std::vector<MX>& out, unsigned seed) {
+    Function f("voc_" + what, in, out);
+    bool expands = true;
+    try { f.expand(); } catch (std::exception&) { expands = false; }
+    CHECK(!expands, what + ": the case must not be expandable (otherwise it does not test the lowering)");
+    Function ref = f.map(n, "serial");
+    auto vin = kkt_like_inputs(ref, n, seed);
+    try {
+      CudaMap::Tape t = CudaMap::lowered_tape(f);
+      check_bits(eval_tape(t, n, vin), eval(ref, vin), "MX vocabulary: " + what);
+    } catch (std::exception& e) {
+      CHECK(false, "MX vocabulary: " + what + " was refused: " + e.what());
+    }
+    return f;
+  };
+  // dense products (reference loops), dense and sparse transposes, reductions
+  check("dense", {K, b, M}, {mtimes(M, x), mtimes(x.T(), M.T()), mtimes(densify(K), x), mtimes(K.T(), x), dot(x, b), norm_2(x),
+                            sumsqr(x), bilin(K, x, b), mmax(x), mmin(K), mmin(x)}, 41);
+  // projections, rank-1 update, casts
+  check("project", {K, b, al}, {project(K, Sparsity::diag(6)), project(x, Sparsity::dense(6, 1)), rank1(densify(K), al, x, b),
+                                sparsity_cast(x, Sparsity::dense(2, 3)), project(K, Sparsity::dense(6, 6)) - 2 * densify(K)}, 43);
+  // get / set nonzeros in their vector and slice forms
+  {
+    MX v = MX::zeros(10, 1);
+    v(Slice(2, 8)) = x;
+    MX u = MX::zeros(10, 1);
+    u(std::vector<casadi_int>{9, 0, 4, 3, 7, 1}) = x;
+    MX k2 = K;
+    k2.nz(Slice(0, 6)) = x;
+    check("nonzeros", {K, b}, {v, u, x(Slice(0, 6, 2)), x.nz(std::vector<casadi_int>{5, 0, 3, 3}), k2, x(Slice(1, 5))}, 44);
+  }
+  // derivative functions of a function with a linear solve (what Map::get_forward / get_reverse map): the forward and the
+  // adjoint sensitivities hold transposed solves, products, projections and add-nonzeros nodes
+  {
+    Function f("voc_ad", {K, b}, {x(Slice(0, 6, 2)), dot(x, x)});
+    for (casadi_int nd : {1, 2}) {
+      Function fw = f.forward(nd), rv = f.reverse(nd);
+      for (const Function& d : {fw, rv}) {
+        Function ref = d.map(n, "serial");
+        auto vin = kkt_like_inputs(ref, n, 50 + static_cast<unsigned>(nd));
+        try {
+          check_bits(eval_tape(CudaMap::lowered_tape(d), n, vin), eval(ref, vin), "MX vocabulary: " + d.name());
+        } catch (std::exception& e) {
+          CHECK(false, "MX vocabulary: " + d.name() + " was refused: " + e.what());
+        }
+      }
+    }
+  }
+  // BASELINE config 5 itself: the derivative functions of [x = solve(K, b); r = K*x - b] for both solvers (transposed QR solves)
+  for (std::string solver : {"ldl", "qr"}) {
+    Function f = ccu_models::kkt_solve(solver);
+    Sparsity ksp = ccu_models::kkt_sparsity();
+    for (const Function& d : {f.forward(1), f.reverse(1)}) {
+      const casadi_int m = 5;
+      Function ref = d.map(m, "serial");
+      auto vin = random_inputs(ref, 61, -1, 1);
+      for (casadi_int i = 0; i < m; ++i) {
+        std::vector<double> v = ccu_models::kkt_values(ksp, i);
+        std::copy(v.begin(), v.end(), vin[0].begin() + i * ksp.nnz());
+      }
+      try {
+        CudaMap::Tape t = CudaMap::lowered_tape(d);
+        auto got = eval_tape(t, m, vin);
+        got.resize(ref.n_out());  // (a trailing failure-count output of the QR lowering is not part of the function)
+        check_bits(got, eval(ref, vin), "MX vocabulary: " + d.name() + " (" + solver + ")");
+      } catch (std::exception& e) {
+        CHECK(false, "MX vocabulary: " + d.name() + " (" + solver + ") was refused: " + e.what());
+      }
+    }
+  }
+  // maps embedded in the function: g.map(3) and the summed form (MapSum) called on pieces of the solution
+  {
+    SX p = SX::sym("p", 2), q = SX::sym("q");
+    Function g("g", {p, q}, {p * q - p(0) / (p(1) + 3), p(0) + q * p(1)});
+    Function G = g.map(3, "serial");
+    std::vector<MX> r = G(std::vector<MX>{reshape(x, 2, 3), b(Slice(0, 3)).T()});
+    // (Function::map with reductions is Map + HorzRepmat + HorzRepsum, function.cpp:797-818; the MapSum node itself comes
+    // from MapSum::create / Function::mapsum)
+    Function Gs = MapSum::create("gs", "serial", g, 3, std::vector<bool>{false, true}, std::vector<bool>{true, false});
+    bool has_mapsum = Gs.class_name() == "MapSum";  // (wrap_as_needed may put the node inside an MX function)
+    for (const std::string& nm : Gs.get_function()) has_mapsum = has_mapsum || Gs.get_function(nm).class_name() == "MapSum";
+    CHECK(has_mapsum, "MapSum::create must give a MapSum node, got " + Gs.class_name());
+    Function Gr = g.map("gr", "serial", 3, std::vector<casadi_int>{1}, std::vector<casadi_int>{0});
+    std::vector<MX> rr = Gr(std::vector<MX>{reshape(x, 2, 3), b(3)});
+    std::vector<MX> rs = Gs(std::vector<MX>{reshape(x, 2, 3), b(3)});
+    check("maps", {K, b}, {r.at(0), r.at(1), rs.at(0), rs.at(1), rr.at(0), rr.at(1)}, 45);
+  }
+  // still refused, loudly: nodes without a numeric evaluation in the reference, side effects
+  {
+    bool threw = false;
+    Function g("voc_bad", {K, b}, {x, norm_inf(b)});
+    try { CudaMap::lowered_tape(g); } catch (std::exception& e) { threw = std::string(e.what()).find("no device lowering") != std::string::npos; }
+    CHECK(threw, "norm_inf has no numeric evaluation and must be refused");
+    threw = false;
+    Function h("voc_mon", {K, b}, {x.monitor("x")});
+    try { CudaMap::lowered_tape(h); } catch (std::exception& e) { threw = std::string(e.what()).find("no device lowering") != std::string::npos; }
+    CHECK(threw, "monitor (a printing side effect) must be refused");
+    threw = false;
+    Function l("voc_lse", {K, b}, {logsumexp(x)});  // (LogSumExp has no eval_sx in the reference: nothing to replay)
+    try { CudaMap::lowered_tape(l); } catch (std::exception& e) { threw = std::string(e.what()).find("no device lowering") != std::string::npos; }
+    CHECK(threw, "logsumexp must be refused");
+  }
+  printf("MX vocabulary around a Linsol call: dense / projections / nonzeros / AD / embedded maps lowered\n");
+}
+
 // ---- the fixed-step integrator ("rk" plugin, casadi/solvers/runge_kutta.cpp) under a map.
 // The oracle (oracle/oracle.c, the checker) evaluates the tape CudaMap lowers the integrator to; the reference's own
 // Integrator::eval through f.map(n, "serial") is the expected result, bit for bit.
@@ -618,6 +753,18 @@ static void kkt_checks() {
     }
     double rel;
     CHECK(compare(eval(F, in), eval(ref, in), &rel) == 0, "kkt_" + solver + ": x and r must be bit-identical to the serial map");
+    // the derivative maps of config 5 stay on the device: Map::get_forward / get_reverse map f.forward(1) / f.reverse(1),
+    // MX functions with (transposed) solves, products, projections and add-nonzeros nodes, lowered node by node
+    for (int rev = 0; rev < 2; ++rev) {
+      Function dref = rev ? ref.reverse(1) : ref.forward(1), dF = rev ? F.reverse(1) : F.forward(1);
+      bool has_cuda = false;
+      for (const std::string& nm : dF.get_function()) has_cuda = has_cuda || dF.get_function(nm).is_a("CudaMap", true);
+      CHECK(has_cuda || dF.is_a("CudaMap", true), std::string(rev ? "reverse" : "forward") + " of the kkt cuda map must call a CudaMap");
+      auto din = random_inputs(dref, 71 + rev, -1, 1);
+      std::copy(in[0].begin(), in[0].end(), din[0].begin());
+      CHECK(compare(eval(dF, din), eval(dref, din), &rel) == 0,
+            "kkt_" + solver + std::string(rev ? " reverse(1)" : " forward(1)") + " of the cuda map must be bit-identical to the serial map's");
+    }
     if (solver == "qr") {
       // a singular instance makes LinsolQr::nfact fail (linsol_qr.cpp:146-163) and the map return 1
       for (casadi_int k = 0; k < sp.nnz(); ++k) in[0][7 * sp.nnz() + k] = 0;
@@ -651,6 +798,7 @@ int main(int argc, char** argv) {
     host_side_checks();
     integrator_lowering_checks();
     newton_lowering_checks();
+    mx_vocabulary_checks();
     if (no_gpu) no_gpu_checks(); else { gpu_checks(); kkt_checks(); integrator_gpu_checks(); newton_gpu_checks(); }
   } catch (std::exception& e) {
     printf("FAIL: unexpected exception: %s\n", e.what());
