@@ -201,6 +201,13 @@ class HostRegistry {
       }
     }
     if (host_ptr_is_pinned(p) && host_ptr_is_pinned(static_cast<const char*>(p) + bytes - 1)) return 0;  // the caller's own
+    // a caller that presents new buffers at every call (the DM API) must not accumulate registrations: past a few dozen
+    // per owner the automatic mode goes back to staging
+    if (owner != nullptr) {
+      size_t held = 0;
+      for (const auto& e : map_) held += e.second.owner == owner;
+      if (held >= kMaxPerOwner) return 1;
+    }
     const cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable);
     if (e != cudaSuccess) { cudaGetLastError(); return 1; }  // (overlaps a foreign registration, locked-memory limit, ...)
     map_[a] = Entry{bytes, owner};
@@ -233,6 +240,7 @@ class HostRegistry {
   }
 
  private:
+  static constexpr size_t kMaxPerOwner = 64;
   struct Entry { size_t bytes; const void* owner; };
   std::mutex mu_;
   std::map<uintptr_t, Entry> map_;
@@ -438,6 +446,7 @@ void jit_options_from_env(ccu::JitOptions* o) {
   if (const char* p = getenv("CCU_JIT_FASTOPS")) o->fastops = atoi(p);
   if (const char* p = getenv("CCU_JIT_RING_INPUTS")) o->ring_inputs = atoi(p);
   if (const char* p = getenv("CCU_JIT_ZIGZAG")) o->zigzag = atoi(p);
+  if (const char* p = getenv("CCU_JIT_IOBASE")) o->iobase = atoi(p);
   if (const char* p = getenv("CCU_JIT_STAGE")) o->stage = atoi(p);
   if (const char* p = getenv("CCU_JIT_SPILL")) o->spill = atoi(p);
   if (const char* p = getenv("CCU_JIT_REGVALS")) o->reg_values = atoi(p);

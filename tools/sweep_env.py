@@ -1,6 +1,6 @@
 """Sweep of specialisation knobs given as environment settings, one fresh tape per setting (run under gpurun):
 device-resident SoA data, best of 3 after a warm-up, every setting must reproduce the bits of the first one.
-usage: sweep_env.py <budget_s> <tape>[@N] "<K=V K=V ...>" ["<K=V ...>" ...]      ("" = the automatic plan)
+usage: sweep_env.py <budget_s> <tape>[@N][,<tape>...] "<K=V K=V ...>" ["<K=V ...>" ...]      ("" = the automatic plan)
   tape: a golden tape name, or "kkt" = BASELINE config 5 as CudaMap lowers it (bench.kkt_tape: LDL + solve + residual)."""
 import json
 import os
@@ -28,9 +28,13 @@ def make(name):
 
 def main():
     budget = float(sys.argv[1])
-    name, _, n = sys.argv[2].partition("@")
+    for spec in sys.argv[2].split(","):  # several tapes share one process (one import of torch)
+        sweep(budget, spec, sys.argv[3:] or [""])
+
+
+def sweep(budget, spec, settings):
+    name, _, n = spec.partition("@")
     N = int(n) if n else SIZES[name]
-    settings = sys.argv[3:] or [""]
     dev = torch.device("cuda:0")
     d_in = d_out = None
     ref = None
