@@ -59,7 +59,7 @@ struct JitOptions {
   int compile_threads = 0;  // 0 = hardware concurrency (max 32)
   long long tile = 0;     // instances per tile (0 = automatic)
   int streams = 1;        // tiles in flight at once (each on its own stream and scratch region)
-  int iobase = 0;         // flat kernels compute the per-instance base address and the byte stride of every operand once at entry
+  int iobase = 1;         // flat kernels compute the per-instance base address and the byte stride of every operand once at entry
                           // (an access is base + k * stride) instead of i * si + k * sk in 64 bits per access
   int zigzag = 1;         // odd kernels of the chain walk the tile's CTAs in reverse order (L2 reuse across kernels)
   std::string cache_dir;  // compiled cubins are cached here ("" = $CCU_JIT_CACHE or ~/.cache/casadi_cuda)
