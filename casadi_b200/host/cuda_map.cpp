@@ -187,9 +187,54 @@ namespace casadi {
                         "Map 'cuda': " + std::string(lib.last_error()));
           ccu_int bad = op(OP_NE, nullity, cst(0.));
           fail_count = fail_count < 0 ? bad : op(OP_ADD, fail_count, bad);
+        } else if (ls.plugin_name() == "tridiag") {
+          tridiag_solve(sp, A, xs, nrhs, tr);
         } else {
           casadi_error("Map 'cuda': linear solver plugin '" + ls.plugin_name()
-                       + "' has no device implementation (supported: ldl, qr)");
+                       + "' has no device implementation (supported: ldl, qr, tridiag)");
+        }
+      }
+
+      // LinsolTridiag::solve (casadi/solvers/linsol_tridiag.cpp:85-151) on handles: the Thomas algorithm with the
+      // plugin's own operation order -- the coefficients c (ctr for the transposed system) once per factorisation, then
+      // d and the back substitution per right-hand side.  The plugin indexes A as A[colind[i] + offset] and so assumes a
+      // tridiagonal pattern without checking it; here a different pattern is refused.  (The reference also computes
+      // c[n-1] from one element past the end of A and never uses it: not traced.)
+      void tridiag_solve(const Sparsity& sp, const Vals& A, Vals& xs, casadi_int nrhs, bool tr) {
+        const casadi_int n = sp.size1();
+        const casadi_int *ci = sp.colind(), *row = sp.row();
+        bool ok = sp.size2() == n && n >= 2;
+        for (casadi_int c = 0; ok && c < n; ++c) {
+          const casadi_int lo = std::max<casadi_int>(c - 1, 0), hi = std::min<casadi_int>(c + 1, n - 1);
+          ok = ci[c + 1] - ci[c] == hi - lo + 1;
+          for (casadi_int k = ci[c]; ok && k < ci[c + 1]; ++k) ok = row[k] == lo + (k - ci[c]);
+        }
+        casadi_assert(ok, "Map 'cuda': linear solver 'tridiag' needs a square tridiagonal pattern with every band entry present, got "
+                      + sp.dim(true));
+        casadi_assert(static_cast<casadi_int>(xs.size()) == n * nrhs, "Map 'cuda': right-hand side size mismatch in 'tridiag'");
+        auto a = [&](casadi_int k) { return A.at(k); };
+        Vals c(n, -1), d(n, -1);
+        // denominator of row i, as the plugin writes it in both loops
+        auto denom = [&](casadi_int i) {
+          if (tr) return op(OP_SUB, a(ci[i] + 1), op(OP_MUL, a(ci[i] + 0), c[i - 1]));
+          return i == 1 ? op(OP_SUB, a(ci[1] + 1), op(OP_MUL, a(ci[0] + 1), c[0]))
+                        : op(OP_SUB, a(ci[i] + 1), op(OP_MUL, a(ci[i - 1] + 2), c[i - 1]));
+        };
+        c[0] = tr ? op(OP_DIV, a(ci[0] + 1), a(ci[0] + 0)) : op(OP_DIV, a(ci[1] + 0), a(ci[0] + 0));
+        for (casadi_int i = 1; i + 1 < n; ++i) {
+          const ccu_int den = denom(i);
+          c[i] = tr ? op(OP_DIV, a(ci[i] + 2), den) : op(OP_DIV, a(ci[i + 1] + 0), den);
+        }
+        for (casadi_int k = 0; k < nrhs; ++k) {
+          ccu_int* x = xs.data() + k * n;
+          d[0] = op(OP_DIV, x[0], a(ci[0] + 0));
+          for (casadi_int i = 1; i < n; ++i) {
+            const ccu_int den = denom(i);
+            const ccu_int sub = tr ? a(ci[i] + 0) : (i == 1 ? a(ci[0] + 1) : a(ci[i - 1] + 2));
+            d[i] = op(OP_DIV, op(OP_SUB, x[i], op(OP_MUL, sub, d[i - 1])), den);
+          }
+          x[n - 1] = d[n - 1];
+          for (casadi_int i = n - 2; i >= 0; --i) x[i] = op(OP_SUB, d[i], op(OP_MUL, c[i], x[i + 1]));
         }
       }
 

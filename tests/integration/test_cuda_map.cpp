@@ -193,6 +193,27 @@ static void mx_vocabulary_checks() {
       }
     }
   }
+  // the "tridiag" plugin (casadi/solvers/linsol_tridiag.cpp: the Thomas algorithm): plain, transposed, two right-hand sides,
+  // and the derivative functions
+  {
+    MX B2 = MX::sym("B2", 6, 2);
+    Function ft = check("tridiag", {K, b, B2}, {solve(K, b, "tridiag"), solve(K.T(), b, "tridiag"), solve(K, B2, "tridiag"),
+                                               mtimes(K, solve(K, b, "tridiag")) - b}, 46);
+    for (const Function& d : {ft.forward(1), ft.reverse(1)}) {
+      Function ref = d.map(n, "serial");
+      auto vin = kkt_like_inputs(ref, n, 47);
+      try {
+        check_bits(eval_tape(CudaMap::lowered_tape(d), n, vin), eval(ref, vin), "MX vocabulary: " + d.name());
+      } catch (std::exception& e) {
+        CHECK(false, "MX vocabulary: " + d.name() + " was refused: " + e.what());
+      }
+    }
+    bool threw = false;
+    MX Kw = MX::sym("Kw", Sparsity::banded(6, 2));
+    Function bad("voc_tri_bad", {Kw, b}, {solve(Kw, b, "tridiag")});
+    try { CudaMap::lowered_tape(bad); } catch (std::exception& e) { threw = std::string(e.what()).find("tridiagonal pattern") != std::string::npos; }
+    CHECK(threw, "a pattern that is not tridiagonal must be refused by the tridiag lowering");
+  }
   // BASELINE config 5 itself: the derivative functions of [x = solve(K, b); r = K*x - b] for both solvers (transposed QR solves)
   for (std::string solver : {"ldl", "qr"}) {
     Function f = ccu_models::kkt_solve(solver);
