@@ -384,7 +384,31 @@ namespace casadi {
             Vals r(a.size());
             for (size_t e = 0; e < a.size(); ++e) r[e] = op(static_cast<int>(o), a[e]);
             w[out.at(0)] = r;
-          } else if (o == OP_TRANSPOSE || o == OP_PROJECT || o == OP_DOT || o == OP_BILIN || o == OP_RANK1 || o == OP_NORMF
+          } else if (o == OP_DOT || o == OP_NORMF || o == OP_NORM1 || o == OP_NORMINF) {
+            // casadi_dot / casadi_norm_2 / casadi_norm_1 / casadi_norm_inf (runtime/): the accumulator starts from an
+            // explicit zero, as in the numeric evaluation (0 + (-0) is +0; an SX expansion would drop the addition)
+            const Vals& a = W(in.at(0));
+            const Vals& c = o == OP_DOT ? W(in.at(1)) : a;
+            casadi_assert(a.size() == c.size(), "Map 'cuda': operand sizes of " + x.class_name() + " differ");
+            ccu_int r = cst(0.);
+            for (size_t e = 0; e < a.size(); ++e) {
+              if (o == OP_NORM1) r = op(OP_ADD, r, op(OP_FABS, a[e]));
+              else if (o == OP_NORMINF) r = op(OP_FMAX, r, op(OP_FABS, a[e]));
+              else r = op(OP_ADD, r, op(OP_MUL, a[e], c[e]));
+            }
+            if (o == OP_NORMF) r = op(OP_SQRT, r);
+            w[out.at(0)] = Vals(1, r);
+          } else if (o == OP_BILIN) {
+            // casadi_bilin (runtime/casadi_bilin.hpp): ret = 0; ret += x[rr]*A[el]*y[cc] column by column
+            const Vals &A = W(in.at(0)), &xx = W(in.at(1)), &yy = W(in.at(2));
+            const Sparsity& spA = x.dep(0).sparsity();
+            const casadi_int *colind = spA.colind(), *row = spA.row();
+            ccu_int r = cst(0.);
+            for (casadi_int cc = 0; cc < spA.size2(); ++cc)
+              for (casadi_int el = colind[cc]; el < colind[cc + 1]; ++el)
+                r = op(OP_ADD, r, op(OP_MUL, op(OP_MUL, xx.at(row[el]), A.at(el)), yy.at(cc)));
+            w[out.at(0)] = Vals(1, r);
+          } else if (o == OP_TRANSPOSE || o == OP_PROJECT || o == OP_RANK1
                      || o == OP_SETNONZEROS || o == OP_ADDNONZEROS || o == OP_MMIN || o == OP_MMAX || o == OP_SPARSITY_CAST
                      || o == OP_LIFT) {
             node_sx(f, x, in, out, w);
