@@ -268,6 +268,58 @@ static void mx_vocabulary_checks() {
   printf("MX vocabulary around a Linsol call: dense / projections / nonzeros / AD / embedded maps lowered\n");
 }
 
+// ---- the tape export on the constructs the reference's own function / SX / MX tests build (test/python/function.py,
+// sx.py, mx.py): what `f.map(n, "cuda")` hands to the device must evaluate -- here through the oracle, on the host, where
+// the transcendentals are the reference's own libm -- to the bits of `f.map(n, "serial")`.
+static void export_checks() {
+  const casadi_int n = 24;
+  int cases = 0;
+  auto check = [&](const Function& f, double lo, double hi, unsigned seed) {
+    Function ref = f.map(n, "serial");
+    auto vin = random_inputs(ref, seed, lo, hi);
+    try {
+      CudaMap::Tape t = CudaMap::lowered_tape(f);
+      check_bits(eval_tape(t, n, vin), eval(ref, vin), "tape export: " + f.name());
+      ++cases;
+    } catch (std::exception& e) {
+      CHECK(false, "tape export: " + f.name() + " was refused: " + e.what());
+    }
+  };
+  SX x = SX::sym("x"), y = SX::sym("y", 2), z = SX::sym("z", 2, 2), v = SX::sym("v", Sparsity::upper(3));
+  // test_map_node's function and variations of its signature: sparse and empty operands, repeated / constant / pass-through outputs
+  check(Function("sig0", {x, y, z, v}, {mtimes(z, y) + x, sin(y * x).T(), v / x}), 0.5, 1.5, 1);
+  check(Function("sig1", {x, SX::sym("e", 0, 0), y}, {x, x, SX(2, 1), y, SX::zeros(Sparsity(3, 3)), 1 + SX::zeros(2, 2)}), -1, 1, 2);
+  check(Function("sig2", {v}, {v.T(), mtimes(v, v), SX::triu(mtimes(v.T(), v)), diag(v), v(Slice(), 1)}), -1, 1, 3);
+  check(Function("sig3", {z, y}, {SX::solve(z + 3 * SX::eye(2), y), inv(z + 3 * SX::eye(2)), det(z), trace(z), norm_fro(z), sum1(z), sum2(z)}), 0.2, 1, 4);
+  // branches and comparisons (sx.py: if_else, logic; calculus.hpp semantics of sign / fmin / fmax / copysign on the edges)
+  check(Function("br0", {x, y}, {if_else(x > 0, y(0) * x, y(1) - x), if_else_zero(y(0) <= y(1), x), x < y, x == floor(x), !(x > 0) || (y(0) > 0)}), -1, 1, 5);
+  check(Function("br1", {x, y}, {fmin(x, y), fmax(y, x), sign(y), fabs(y) * copysign(x, y(1)), floor(3 * y), ceil(3 * y), fmod(7 * y, x), remainder(7 * y, x)}), -1, 1, 6);
+  // powers and roots with constant and variable exponents (sx.py test_pow / constpow simplifications)
+  check(Function("pw0", {x, y}, {pow(x, 2), pow(x, 3), pow(x, 0.5), pow(x, -1), pow(x, -2.5), pow(x, y), constpow(x, SX(1.7)), pow(2, y), sqrt(x) * sq(y), 1 / y, x / y / y}), 0.3, 2, 7);
+  // the transcendental set
+  check(Function("tr0", {x, y}, {exp(y), log(x), sin(y), cos(y), tan(y), asin(y / 3), acos(y / 3), atan(y), atan2(y, x), sinh(y), cosh(y), tanh(y),
+                                 asinh(y), acosh(1 + x), atanh(y / 3), erf(y), erfinv(y / 3), log1p(x), expm1(y), hypot(x, y)}), 0.2, 1.5, 8);
+  // AD products of a small dynamics function, as Function::forward / reverse / jacobian / hessian build them
+  {
+    SX s = SX::sym("s", 3), u = SX::sym("u");
+    SX rhs = vertcat(s(1), -sin(s(0)) * s(2) - 0.1 * s(1) + u, (u - s(2)) / (1 + s(0) * s(0)));
+    Function dyn("dyn", {s, u}, {s + 0.05 * rhs, dot(rhs, rhs)});
+    check(dyn, -1, 1, 9);
+    check(dyn.forward(2), -1, 1, 10);
+    check(dyn.reverse(2), -1, 1, 11);
+    check(dyn.jacobian(), -1, 1, 12);
+    check(Function("hdyn", {s, u}, {hessian(dot(rhs, rhs), s), gradient(dot(rhs, rhs), s)}), -1, 1, 13);
+    // towers: mapaccum, fold, a nested map, an MX wrapper that calls the SX function twice
+    check(dyn.mapaccum("acc", 5, std::vector<casadi_int>{0}, std::vector<casadi_int>{0}), -1, 1, 14);
+    check(dyn.fold(4), -1, 1, 15);
+    check(dyn.map(3, "serial"), -1, 1, 16);
+    MX ms = MX::sym("s", 3), mu = MX::sym("u");
+    std::vector<MX> r1 = dyn(std::vector<MX>{ms, mu}), r2 = dyn(std::vector<MX>{r1.at(0), mu * r1.at(1)});
+    check(Function("wrap", {ms, mu}, {r2.at(0), r1.at(1) - r2.at(1), vertcat(r1.at(0), r2.at(0))(Slice(1, 5))}), -1, 1, 17);
+  }
+  printf("tape export: %d reference-style functions evaluate to the bits of the serial map\n", cases);
+}
+
 // ---- the fixed-step integrator ("rk" plugin, casadi/solvers/runge_kutta.cpp) under a map.
 // The oracle (oracle/oracle.c, the checker) evaluates the tape CudaMap lowers the integrator to; the reference's own
 // Integrator::eval through f.map(n, "serial") is the expected result, bit for bit.
@@ -823,6 +875,7 @@ int main(int argc, char** argv) {
     integrator_lowering_checks();
     newton_lowering_checks();
     mx_vocabulary_checks();
+    export_checks();
     if (no_gpu) no_gpu_checks(); else { gpu_checks(); kkt_checks(); integrator_gpu_checks(); newton_gpu_checks(); }
   } catch (std::exception& e) {
     printf("FAIL: unexpected exception: %s\n", e.what());
