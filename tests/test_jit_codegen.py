@@ -180,3 +180,41 @@ def test_jit_plan_reports_cross_segment_traffic():
         for part in s.split("CCU_ST(")[1:]:
             if part[0].isdigit():
                 written.add(int(part.split(",")[0]))
+
+
+def test_operand_bases_cut_the_integer_instructions(monkeypatch):
+    """Per-operand base addresses (JitOptions::iobase, on by default): the kernels of an operand-heavy tape -- the
+    mapaccum rollout, 400 input nonzeros -- compile (NVRTC, sm_100a, no GPU) to fewer SASS instructions than with the
+    address of every access computed as i*si + k*sk, without spilling more.  tools/sass_stats.py is the same accounting;
+    the timing of the A/B on a B200 is profiles/r2_sweep_iobase.jsonl."""
+    import collections
+    import glob
+    import re
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    L = capi.lib()
+    monkeypatch.setenv("CCU_JIT_CACHE", "off")
+
+    def count(iobase):
+        monkeypatch.setenv("CCU_JIT_IOBASE", str(iobase))
+        t = CudaTape(load_tape("mc"), device=-1)
+        ops, local = collections.Counter(), 0
+        with tempfile.TemporaryDirectory() as tmp:
+            n = L.ccu_tape_jit_compile_check(t.handle, tmp.encode())
+            if n < 0 and "not loadable" in capi.last_error():
+                pytest.skip("libnvrtc not present on this box")
+            assert n > 0, capi.last_error()
+            for f in glob.glob(os.path.join(tmp, "*.cubin")):
+                sass = subprocess.run(["cuobjdump", "-sass", f], capture_output=True, text=True).stdout
+                for line in sass.splitlines():
+                    m = re.search(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+                    if m:
+                        ops[m.group(1).split(".")[0]] += 1
+        return sum(ops.values()), ops["LDL"] + ops["STL"], ops["DADD"] + ops["DMUL"] + ops["DFMA"]
+
+    plain, plain_local, plain_fp64 = count(0)
+    based, based_local, based_fp64 = count(1)
+    assert based_fp64 == plain_fp64          # the arithmetic is untouched
+    assert based < 0.93 * plain, (based, plain)
+    assert based_local <= plain_local + 8, (based_local, plain_local)
