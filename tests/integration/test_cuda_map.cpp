@@ -517,6 +517,38 @@ static void newton_lowering_checks() {
   }
 }
 
+// The derivative functions of a rootfinder (Rootfinder::get_forward / get_reverse, rootfinder.cpp:318-345, 454-560) do not
+// call the solver: they take the nominal solution as an input and are plain MX functions -- the oracle's derivative
+// functions, jac_g_x and a (transposed) Linsol solve -- which the lowering handles since its vocabulary is closed under AD.
+// So rf.map(n, "cuda").forward(k) / .reverse(k) map them on the device (Map::get_forward); here on the host, bit for bit.
+static void newton_derivative_lowering_checks() {
+  const casadi_int n = 32;
+  for (int which : {1, 2}) {
+    Function rf = newton_case(which);
+    for (int rev = 0; rev < 2; ++rev) {
+      for (casadi_int nd : {1, 3}) {
+        Function d = rev ? rf.reverse(nd) : rf.forward(nd);
+        Function ref = d.map(n, "serial");
+        // nominal inputs as for the solver, the nominal outputs from the solver itself, seeds U(-1, 1)
+        auto nom = newton_inputs(which, n);
+        auto sol = eval(rf.map(n, "serial"), nom);
+        auto vin = random_inputs(ref, 301 + which + 7 * rev, -1, 1);
+        for (casadi_int j = 0; j < rf.n_in(); ++j) vin[j] = nom[j];
+        for (casadi_int j = 0; j < rf.n_out(); ++j) if (!vin[rf.n_in() + j].empty()) vin[rf.n_in() + j] = sol[j];
+        try {
+          CudaMap::Tape t = CudaMap::lowered_tape(d);
+          auto got = eval_tape(t, n, vin);
+          got.resize(ref.n_out());  // (a trailing failure-count output of the QR lowering is not part of the function)
+          check_bits(got, eval(ref, vin), "lowered " + d.name() + " of newton case " + str(which));
+        } catch (std::exception& e) {
+          CHECK(false, "lowering of " + d.name() + " of newton case " + str(which) + " was refused: " + e.what());
+        }
+      }
+    }
+  }
+  printf("rootfinder derivative functions (forward / reverse, 1 and 3 directions) lowered bit-exactly\n");
+}
+
 static void newton_gpu_checks() {
   for (int which : {0, 1, 3}) {  // (case 2 calls atan: device libm, compared with a tolerance below)
     for (casadi_int n : {200, 5000}) {
@@ -874,6 +906,7 @@ int main(int argc, char** argv) {
     host_side_checks();
     integrator_lowering_checks();
     newton_lowering_checks();
+    newton_derivative_lowering_checks();
     mx_vocabulary_checks();
     export_checks();
     if (no_gpu) no_gpu_checks(); else { gpu_checks(); kkt_checks(); integrator_gpu_checks(); newton_gpu_checks(); }
