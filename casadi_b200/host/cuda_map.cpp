@@ -500,9 +500,9 @@ namespace casadi {
         const std::string who = "Map 'cuda': integrator '" + f.name() + "' (" + f.class_name() + "): ";
         casadi_assert(I->has_function("step"), who + "implicit step functions (collocation) have no device lowering");
         casadi_assert(I->ne_ == 0, who + "events (zero-crossing functions) have no device lowering");
-        casadi_assert(I->nrx_ == 0 && I->nadj_ == 0, who + "backward states (adjoint sensitivities) have no device "
-                      "lowering; use forward mode or map the derivative of the simplified integrator");
-        casadi_assert(I->nz_ == 0, who + "algebraic variables have no device lowering");
+        casadi_assert(I->nrx_ == 0 || I->nfwd_ == 0, who + "forward sensitivities of backward states (forward-over-adjoint) "
+                      "have no device lowering");
+        casadi_assert(I->nz_ == 0 && I->nrz_ == 0, who + "algebraic variables have no device lowering");
         const Function& F = I->get_function("step");
         const casadi_int nfwd = I->nfwd_;
         Function dF;
@@ -518,6 +518,10 @@ namespace casadi {
         };
         Vals x = take(INTEGRATOR_X0, 0, nx), p = take(INTEGRATOR_P, 0, np), q(nq, zero);
         Vals v(nv, cst(std::numeric_limits<double>::quiet_NaN()));  // FixedStepIntegrator::reset, :2230
+        // the state after every step, for the backward sweep (m->x_tape, m->v_tape; advance_noevent :2066-2070)
+        const bool backward = I->nrx_ > 0;
+        std::vector<Vals> x_tape, v_tape;
+        if (backward) x_tape.push_back(x);
         double t = I->t0_;
         for (casadi_int k = 0; k < nt; ++k) {
           const double t_next = I->tout_.at(k);
@@ -560,11 +564,97 @@ namespace casadi {
             // casadi_axpy(nq_, 1., q_prev, q)
             const ccu_int one = cst(1.);
             for (casadi_int i = 0; i < nq; ++i) q[i] = op(OP_ADD, q[i], op(OP_MUL, one, q_prev[i]));
+            if (backward) { x_tape.push_back(x); v_tape.push_back(v); }
           }
           t = t_next;
           if (res.at(INTEGRATOR_XF)) std::copy(x.begin(), x.end(), res[INTEGRATOR_XF]->begin() + k * nx);
           if (res.at(INTEGRATOR_QF)) std::copy(q.begin(), q.end(), res[INTEGRATOR_QF]->begin() + k * nq);
         }
+        if (backward) backward_sweep(f, I, arg, res, x_tape, v_tape, p);
+      }
+
+      // The backward integration of Integrator::eval (integrator.cpp:459-517) for a fixed-step integrator with backward
+      // states (the adjoint integrator Integrator::get_reverse creates): resetB, then from the last output time to t0 the
+      // impulse of the adjoint seeds (impulseB, :2254-2271) and the backward steps of the interval (retreat, :2081-2117;
+      // stepB :2152-2176 calls the plugin's adj<nadj>_step with the states the forward sweep left on its tape).  The
+      // reference adds an impulse only when a seed of that output time is nonzero and integrates backward only once some
+      // impulse has occurred; per instance of a map these are data, so both become bit-exact selects on the 0/1 flags.
+      void backward_sweep(const Function& f, const FixedStepIntegrator* I, const std::vector<const Vals*>& arg,
+                          std::vector<Vals*>& res, const std::vector<Vals>& x_tape, const std::vector<Vals>& v_tape,
+                          const Vals& p) {
+        const casadi_int nadj = I->nadj_, nrx = I->nrx_, nrq = I->nrq_, nuq = I->nuq_, nrp = I->nrp_, nrv = I->nrv_;
+        const casadi_int nu = I->nu_, nt = I->nt();
+        const Function& B = I->get_function(FunctionInternal::reverse_name("step", nadj));
+        const ccu_int zero = cst(0.), one = cst(1.), minus_one = cst(-1.);
+        auto take = [&](casadi_int j, casadi_int off, casadi_int n) {
+          Vals r(n, zero);
+          if (arg.at(j)) for (casadi_int i = 0; i < n; ++i) r[i] = arg[j]->at(off + i);
+          return r;
+        };
+        auto sel = [&](ccu_int c, ccu_int a, ccu_int b2) {
+          ccu_int h = lib.builder_select(b, c, a, b2);
+          casadi_assert(h >= 0, "Map 'cuda': " + std::string(lib.last_error()));
+          return h;
+        };
+        // resetB (:2239-2252)
+        Vals adj_q(nrp, zero), adj_x(nrx, zero), adj_p(nrq, zero), adj_u(nuq, zero);
+        const Vals rv(nrv, zero);  // (only algebraic variables put an impulse on it, and it is cleared after every step)
+        ccu_int any_impulse = zero;
+        std::vector<Vals> adj_u_out(nt, Vals(nuq, zero));
+        for (casadi_int k = nt; k-- > 0; ) {
+          const double t = I->tout_.at(k), t_next = k == 0 ? I->t0_ : I->tout_.at(k - 1);
+          const Vals seed_x = take(INTEGRATOR_ADJ_XF, k * nrx, nrx), seed_q = take(INTEGRATOR_ADJ_QF, k * nrp, nrp);
+          const Vals u = take(INTEGRATOR_U, k * nu, nu);
+          // !all_zero(adj_xf) || !all_zero(rp)   (:2757-2766: v[i] != 0.)
+          ccu_int nz = zero;
+          if (arg.at(INTEGRATOR_ADJ_XF)) for (casadi_int i = 0; i < nrx; ++i) nz = op(OP_OR, nz, op(OP_NE, seed_x[i], zero));
+          if (arg.at(INTEGRATOR_ADJ_QF)) for (casadi_int i = 0; i < nrp; ++i) nz = op(OP_OR, nz, op(OP_NE, seed_q[i], zero));
+          // impulseB: casadi_axpy(n, 1., seed, state), only when a seed is nonzero
+          if (arg.at(INTEGRATOR_ADJ_QF))
+            for (casadi_int i = 0; i < nrp; ++i) adj_q[i] = sel(nz, op(OP_ADD, adj_q[i], op(OP_MUL, one, seed_q[i])), adj_q[i]);
+          if (arg.at(INTEGRATOR_ADJ_XF))
+            for (casadi_int i = 0; i < nrx; ++i) adj_x[i] = sel(nz, op(OP_ADD, adj_x[i], op(OP_MUL, one, seed_x[i])), adj_x[i]);
+          any_impulse = op(OP_OR, any_impulse, nz);
+          // retreat, as if an impulse had occurred; what it leaves is selected below
+          Vals rx = adj_x, rp = adj_p, ru = adj_u;
+          const casadi_int nj = I->disc_.at(k + 1) - I->disc_.at(k);
+          const double h = (t - t_next) / nj;
+          for (casadi_int j = nj; j-- > 0; ) {
+            const double tj = t_next + j * h;
+            const Vals x_prev = rx, p_prev = rp, u_prev = ru;
+            const casadi_int tapeind = I->disc_.at(k) + j;
+            const Vals tv(1, cst(tj)), hv(1, cst(h));
+            std::vector<const Vals*> a(B.n_in(), nullptr);
+            a[BSTEP_T] = &tv; a[BSTEP_H] = &hv; a[BSTEP_X0] = &x_tape.at(tapeind); a[BSTEP_P] = &p; a[BSTEP_U] = &u;
+            a[BSTEP_OUT_XF] = &x_tape.at(tapeind + 1); a[BSTEP_OUT_VF] = &v_tape.at(tapeind);
+            a[BSTEP_ADJ_XF] = &x_prev; a[BSTEP_ADJ_VF] = &rv; a[BSTEP_ADJ_QF] = &adj_q;
+            // (outputs that are structurally empty in adj_step stay zero: issue #3353, :2171-2174)
+            Vals ox(nrx, zero), opar(nrq, zero), ou(nuq, zero);
+            std::vector<Vals*> r(B.n_out(), nullptr);
+            r[BSTEP_ADJ_X0] = &ox; r[BSTEP_ADJ_P] = &opar; r[BSTEP_ADJ_U] = &ou;
+            call(B, a, r);
+            rx = ox;
+            for (casadi_int i = 0; i < nrq; ++i) rp[i] = op(OP_ADD, opar[i], op(OP_MUL, one, p_prev[i]));
+            for (casadi_int i = 0; i < nuq; ++i) ru[i] = op(OP_ADD, ou[i], op(OP_MUL, one, u_prev[i]));
+          }
+          // if (any_impulse) the states are what retreat left and adj_u of this interval is the running sum; otherwise the
+          // states are untouched and the output is cleared
+          for (casadi_int i = 0; i < nrx; ++i) adj_x[i] = sel(any_impulse, rx[i], adj_x[i]);
+          for (casadi_int i = 0; i < nrq; ++i) adj_p[i] = sel(any_impulse, rp[i], adj_p[i]);
+          for (casadi_int i = 0; i < nuq; ++i) adj_u[i] = sel(any_impulse, ru[i], adj_u[i]);
+          for (casadi_int i = 0; i < nuq; ++i) adj_u_out[k][i] = sel(any_impulse, adj_u[i], zero);
+          if (k == 0) {
+            if (res.at(INTEGRATOR_ADJ_X0)) for (casadi_int i = 0; i < nrx; ++i) res[INTEGRATOR_ADJ_X0]->at(i) = sel(any_impulse, adj_x[i], zero);
+            if (res.at(INTEGRATOR_ADJ_P)) for (casadi_int i = 0; i < nrq; ++i) res[INTEGRATOR_ADJ_P]->at(i) = sel(any_impulse, adj_p[i], zero);
+          }
+        }
+        // adj_u per grid point, not cumulative (:2509-2515): adj_u[k] += -1 * adj_u[k+1], front to back
+        for (casadi_int k = 0; k + 1 < nt; ++k)
+          for (casadi_int i = 0; i < nuq; ++i)
+            adj_u_out[k][i] = op(OP_ADD, adj_u_out[k][i], op(OP_MUL, minus_one, adj_u_out[k + 1][i]));
+        if (res.at(INTEGRATOR_ADJ_U))
+          for (casadi_int k = 0; k < nt; ++k) std::copy(adj_u_out[k].begin(), adj_u_out[k].end(), res[INTEGRATOR_ADJ_U]->begin() + k * nuq);
+        (void)f;
       }
 
       // n evaluations of g over consecutive blocks of the operands (Map / MapSum); reduce_in: one shared block,

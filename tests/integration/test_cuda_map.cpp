@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <random>
 #include <unistd.h>
 
@@ -410,12 +411,46 @@ static void integrator_lowering_checks() {
     auto in = integrator_inputs(ref, 31);
     check_bits(eval_tape(CudaMap::lowered_tape(I), n, in), eval(ref, in), "simplified rk integrator");
   }
-  // adjoint sensitivities (backward states) are refused loudly
+  // adjoint sensitivities: the adjoint integrator Integrator::get_reverse creates has backward states; its backward sweep
+  // (impulses of the seeds at the output times, retreat through the forward sweep's tape) is replayed with the reference's
+  // data-dependent shortcuts -- no impulse for an all-zero seed, no backward integration before the first impulse -- as
+  // bit-exact selects.  One and several output times, one and two adjoint directions, instances with all seeds zero, with
+  // the seeds of the last output time zero, and with a NaN seed.
+  for (int variant = 0; variant < 2; ++variant) {
+    std::vector<double> tout = variant == 0 ? std::vector<double>{1.0} : std::vector<double>{0.4, 0.9, 1.35};
+    Function I = rk_integrator("intg_adj" + str(variant), tout, 7);
+    for (casadi_int nadj : {1, 2}) {
+      Function dI = I.reverse(nadj);
+      Function ref = dI.map(n, "serial");
+      auto in = integrator_inputs(ref, 41 + variant + 10 * static_cast<unsigned>(nadj));
+      const casadi_int first_seed = I.n_in() + I.n_out();
+      for (casadi_int j = first_seed; j < dI.n_in(); ++j) {
+        const casadi_int nz = dI.nnz_in(j);
+        for (casadi_int i : {0, 5}) std::fill(in[j].begin() + i * nz, in[j].begin() + (i + 1) * nz, 0.0);  // no seed at all
+      }
+      {  // instance 7: nothing at the last output time (the backward integration starts one interval earlier)
+        const casadi_int j = first_seed + INTEGRATOR_XF, nz = dI.nnz_in(j), nx = 2, nt = static_cast<casadi_int>(tout.size());
+        for (casadi_int d = 0; d < nadj; ++d)
+          for (casadi_int e = 0; e < nx; ++e) in[j][7 * nz + d * nx * nt + (nt - 1) * nx + e] = 0.0;
+        const casadi_int jq = first_seed + INTEGRATOR_QF, nzq = dI.nnz_in(jq);
+        for (casadi_int d = 0; d < nadj; ++d) in[jq][7 * nzq + d * nt + (nt - 1)] = 0.0;
+        in[j][9 * nz] = std::numeric_limits<double>::quiet_NaN();  // instance 9: a NaN seed is "not zero"
+      }
+      try {
+        CudaMap::Tape t = CudaMap::lowered_tape(dI);
+        check_bits(eval_tape(t, n, in), eval(ref, in), "lowered reverse(" + str(nadj) + ") of the rk integrator, variant " + str(variant));
+        if (variant == 1 && nadj == 1) printf("rk integrator reverse(1): lowered tape %zu instructions\n", t.op.size());
+      } catch (std::exception& e) {
+        CHECK(false, "reverse(" + str(nadj) + ") of the rk integrator, variant " + str(variant) + " was refused: " + e.what());
+      }
+    }
+  }
+  // forward-over-adjoint (an adjoint integrator augmented with forward sensitivities) is refused loudly
   {
-    Function I = rk_integrator("intg_adj", {1.0}, 4);
+    Function I = rk_integrator("intg_foa", {1.0}, 4);
     bool threw = false;
-    try { CudaMap::lowered_tape(I.reverse(1)); } catch (std::exception& e) { threw = std::string(e.what()).find("no device lowering") != std::string::npos; }
-    CHECK(threw, "reverse mode of an integrator must be refused");
+    try { CudaMap::lowered_tape(I.reverse(1).forward(1)); } catch (std::exception& e) { threw = std::string(e.what()).find("no device lowering") != std::string::npos; }
+    CHECK(threw, "forward-over-adjoint of an integrator must be refused");
   }
 }
 
