@@ -500,8 +500,6 @@ namespace casadi {
         const std::string who = "Map 'cuda': integrator '" + f.name() + "' (" + f.class_name() + "): ";
         casadi_assert(I->has_function("step"), who + "implicit step functions (collocation) have no device lowering");
         casadi_assert(I->ne_ == 0, who + "events (zero-crossing functions) have no device lowering");
-        casadi_assert(I->nrx_ == 0 || I->nfwd_ == 0, who + "forward sensitivities of backward states (forward-over-adjoint) "
-                      "have no device lowering");
         casadi_assert(I->nz_ == 0 && I->nrz_ == 0, who + "algebraic variables have no device lowering");
         const Function& F = I->get_function("step");
         const casadi_int nfwd = I->nfwd_;
@@ -582,9 +580,16 @@ namespace casadi {
       void backward_sweep(const Function& f, const FixedStepIntegrator* I, const std::vector<const Vals*>& arg,
                           std::vector<Vals*>& res, const std::vector<Vals>& x_tape, const std::vector<Vals>& v_tape,
                           const Vals& p) {
-        const casadi_int nadj = I->nadj_, nrx = I->nrx_, nrq = I->nrq_, nuq = I->nuq_, nrp = I->nrp_, nrv = I->nrv_;
+        const casadi_int nadj = I->nadj_, nfwd = I->nfwd_, nrx = I->nrx_, nrq = I->nrq_, nuq = I->nuq_, nrp = I->nrp_, nrv = I->nrv_;
         const casadi_int nu = I->nu_, nt = I->nt();
+        // sizes of the nominal block of every vector (the forward sensitivities of an augmented integrator follow it)
+        const casadi_int nx1 = I->nx1_, np1 = I->np1_, nu1 = I->nu1_, nv1 = I->nv1_, nrv1 = I->nrv1_;
+        const casadi_int nrx1 = I->nrx1_ * nadj, nrq1 = I->nrq1_ * nadj, nuq1 = I->nuq1_ * nadj, nrp1 = I->nrp1_ * nadj;
         const Function& B = I->get_function(FunctionInternal::reverse_name("step", nadj));
+        Function dB;
+        if (nfwd > 0) dB = I->get_function(FunctionInternal::forward_name(FunctionInternal::reverse_name("step", nadj), nfwd));
+        auto head = [](const Vals& v, casadi_int n) { return Vals(v.begin(), v.begin() + n); };
+        auto tail = [](const Vals& v, casadi_int n) { return Vals(v.begin() + n, v.end()); };
         const ccu_int zero = cst(0.), one = cst(1.), minus_one = cst(-1.);
         auto take = [&](casadi_int j, casadi_int off, casadi_int n) {
           Vals r(n, zero);
@@ -624,15 +629,36 @@ namespace casadi {
             const Vals x_prev = rx, p_prev = rp, u_prev = ru;
             const casadi_int tapeind = I->disc_.at(k) + j;
             const Vals tv(1, cst(tj)), hv(1, cst(h));
+            // nominal blocks of the operands (stepB :2155-2176)
+            const Vals x0 = head(x_tape.at(tapeind), nx1), xf = head(x_tape.at(tapeind + 1), nx1), vf = head(v_tape.at(tapeind), nv1),
+                       pp = head(p, np1), uu = head(u, nu1), sx = head(x_prev, nrx1), srv = head(rv, nrv1), sq = head(adj_q, nrp1);
             std::vector<const Vals*> a(B.n_in(), nullptr);
-            a[BSTEP_T] = &tv; a[BSTEP_H] = &hv; a[BSTEP_X0] = &x_tape.at(tapeind); a[BSTEP_P] = &p; a[BSTEP_U] = &u;
-            a[BSTEP_OUT_XF] = &x_tape.at(tapeind + 1); a[BSTEP_OUT_VF] = &v_tape.at(tapeind);
-            a[BSTEP_ADJ_XF] = &x_prev; a[BSTEP_ADJ_VF] = &rv; a[BSTEP_ADJ_QF] = &adj_q;
+            a[BSTEP_T] = &tv; a[BSTEP_H] = &hv; a[BSTEP_X0] = &x0; a[BSTEP_P] = &pp; a[BSTEP_U] = &uu;
+            a[BSTEP_OUT_XF] = &xf; a[BSTEP_OUT_VF] = &vf;
+            a[BSTEP_ADJ_XF] = &sx; a[BSTEP_ADJ_VF] = &srv; a[BSTEP_ADJ_QF] = &sq;
             // (outputs that are structurally empty in adj_step stay zero: issue #3353, :2171-2174)
-            Vals ox(nrx, zero), opar(nrq, zero), ou(nuq, zero);
+            Vals ox(nrx1, zero), opar(nrq1, zero), ou(nuq1, zero);
             std::vector<Vals*> r(B.n_out(), nullptr);
             r[BSTEP_ADJ_X0] = &ox; r[BSTEP_ADJ_P] = &opar; r[BSTEP_ADJ_U] = &ou;
             call(B, a, r);
+            if (nfwd > 0) {
+              // forward sensitivities of the backward step (:2178-2217): the nominal operands and results, then the seeds
+              const Vals fx0 = tail(x_tape.at(tapeind), nx1), fxf = tail(x_tape.at(tapeind + 1), nx1), fvf = tail(v_tape.at(tapeind), nv1),
+                         fp = tail(p, np1), fu = tail(u, nu1), fsx = tail(x_prev, nrx1), fsrv = tail(rv, nrv1), fsq = tail(adj_q, nrp1);
+              std::vector<const Vals*> fa(dB.n_in(), nullptr);
+              for (casadi_int q = 0; q < BSTEP_NUM_IN; ++q) fa[q] = a[q];
+              fa[BSTEP_NUM_IN + BSTEP_ADJ_X0] = &ox; fa[BSTEP_NUM_IN + BSTEP_ADJ_P] = &opar; fa[BSTEP_NUM_IN + BSTEP_ADJ_U] = &ou;
+              const casadi_int o = BSTEP_NUM_IN + BSTEP_NUM_OUT;
+              fa[o + BSTEP_X0] = &fx0; fa[o + BSTEP_P] = &fp; fa[o + BSTEP_U] = &fu; fa[o + BSTEP_OUT_XF] = &fxf; fa[o + BSTEP_OUT_VF] = &fvf;
+              fa[o + BSTEP_ADJ_XF] = &fsx; fa[o + BSTEP_ADJ_VF] = &fsrv; fa[o + BSTEP_ADJ_QF] = &fsq;
+              Vals fox(nrx - nrx1, zero), fopar(nrq - nrq1, zero), fou(nuq - nuq1, zero);
+              std::vector<Vals*> fr(dB.n_out(), nullptr);
+              fr[BSTEP_ADJ_X0] = &fox; fr[BSTEP_ADJ_P] = &fopar; fr[BSTEP_ADJ_U] = &fou;
+              call(dB, fa, fr);
+              ox.insert(ox.end(), fox.begin(), fox.end());
+              opar.insert(opar.end(), fopar.begin(), fopar.end());
+              ou.insert(ou.end(), fou.begin(), fou.end());
+            }
             rx = ox;
             for (casadi_int i = 0; i < nrq; ++i) rp[i] = op(OP_ADD, opar[i], op(OP_MUL, one, p_prev[i]));
             for (casadi_int i = 0; i < nuq; ++i) ru[i] = op(OP_ADD, ou[i], op(OP_MUL, one, u_prev[i]));
