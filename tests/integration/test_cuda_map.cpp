@@ -644,6 +644,35 @@ static void integrator_gpu_checks() {
       check_close(eval(tF, tin), eval(tref, tin), 1e-11, "rk integrator with sin/cos dynamics under map(cuda)");
     }
   }
+  // Device checks of the derivative maps whose lowering is pinned bit for bit on the host (adjoint and second-order
+  // sensitivities of the integrator, forward / reverse of the rootfinder) but which no B200 run of this round has seen:
+  // opt-in (CCU_TEST_DEVICE_EXTRA=1) until one has.
+  if (getenv("CCU_TEST_DEVICE_EXTRA")) {
+    const casadi_int n = 1000;
+    Function I = rk_integrator("intg_gpu_adj", {0.4, 0.9, 1.35}, 7, false, true);
+    for (int which = 0; which < 3; ++which) {
+      Function dI = which == 0 ? I.reverse(1) : which == 1 ? I.reverse(2) : I.reverse(1).forward(1);
+      Function dref = dI.map(n, "serial"), dF = dI.map(n, "cuda");
+      auto din = integrator_inputs(dref, 71 + which);
+      check_bits(eval(dF, din), eval(dref, din), "derivative " + str(which) + " (adjoint / second order) of the rk integrator under map(cuda)");
+    }
+    Function F = I.map(n, "cuda"), ref = I.map(n, "serial");
+    Function Fr = F.reverse(1), Rr = ref.reverse(1);
+    auto rin = integrator_inputs(Rr, 79);
+    check_bits(eval(Fr, rin), eval(Rr, rin), "reverse(1) of map(cuda) of the rk integrator");
+    Function rf = newton_case(1);
+    for (int rev = 0; rev < 2; ++rev) {
+      Function d = rev ? rf.reverse(1) : rf.forward(1);
+      Function dref = d.map(n, "serial"), dF = d.map(n, "cuda");
+      auto nom = newton_inputs(1, n);
+      auto sol = eval(rf.map(n, "serial"), nom);
+      auto vin = random_inputs(dref, 83 + rev, -1, 1);
+      for (casadi_int j = 0; j < rf.n_in(); ++j) vin[j] = nom[j];
+      for (casadi_int j = 0; j < rf.n_out(); ++j) if (!vin[rf.n_in() + j].empty()) vin[rf.n_in() + j] = sol[j];
+      check_bits(eval(dF, vin), eval(dref, vin), std::string(rev ? "reverse" : "forward") + "(1) of the Newton rootfinder under map(cuda)");
+    }
+    printf("extra device checks done\n");
+  }
 }
 
 static void no_gpu_checks() {
