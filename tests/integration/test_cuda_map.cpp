@@ -216,6 +216,20 @@ static void mx_vocabulary_checks() {
     try { CudaMap::lowered_tape(bad); } catch (std::exception& e) { threw = std::string(e.what()).find("tridiagonal pattern") != std::string::npos; }
     CHECK(threw, "a pattern that is not tridiagonal must be refused by the tridiag lowering");
   }
+  // Jacobian and second-order functions of a function with a linear solve (Function::jacobian: multiple right-hand sides,
+  // projections; forward-over-reverse as the Hessian-vector products of an NLP with an embedded solve)
+  {
+    Function f("voc_ad2", {K, b}, {dot(x, x) + bilin(K, x, b), x(Slice(1, 4))});
+    for (const Function& d : {f.jacobian(), f.reverse(1).forward(1), f.forward(1).reverse(1)}) {
+      Function ref = d.map(n, "serial");
+      auto vin = kkt_like_inputs(ref, n, 58);
+      try {
+        check_bits(eval_tape(CudaMap::lowered_tape(d), n, vin), eval(ref, vin), "MX vocabulary: " + d.name());
+      } catch (std::exception& e) {
+        CHECK(false, "MX vocabulary: " + d.name() + " was refused: " + e.what());
+      }
+    }
+  }
   // BASELINE config 5 itself: the derivative functions of [x = solve(K, b); r = K*x - b] for both solvers (transposed QR solves)
   for (std::string solver : {"ldl", "qr"}) {
     Function f = ccu_models::kkt_solve(solver);
