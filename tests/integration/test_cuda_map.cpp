@@ -529,6 +529,15 @@ static Function newton_case(int which) {
     Function f("g2", {x, p}, {g, x(0) * x(1) + p(0)});
     return rootfinder("rf2", "newton", f, Dict{{"max_iter", 60}});
   }
+  if (which == 4 || which == 5) {
+    // a 4-variable system with a symmetric tridiagonal Jacobian: the gradient of sum_i (x_i^4/4 + x_i^2) + sum_i x_i x_{i+1}/2 - p.x,
+    // solved with the "ldl" (4) and the "tridiag" (5) linear solvers
+    SX x = SX::sym("x", 4), p = SX::sym("p", 4);
+    SX g = x * x * x + 2 * x - p;
+    for (int i = 0; i < 3; ++i) { g(i) += x(i + 1) / 2; g(i + 1) += x(i) / 2; }
+    Function f("gtri", {x, p}, {g, dot(x, x)});
+    return rootfinder("rftri" + str(which), "newton", f, Dict{{"linear_solver", which == 4 ? "ldl" : "tridiag"}, {"max_iter", 60}});
+  }
   SX x = SX::sym("x"), y = SX::sym("y");
   Function f("fatan", {x, y}, {atan(x) - y / 4});
   return rootfinder("rfatan", "newton", f, Dict{{"max_iter", 80}});
@@ -543,6 +552,8 @@ static std::vector<std::vector<double>> newton_inputs(int which, casadi_int n) {
     for (casadi_int i = 0; i < n; ++i) in[1].push_back(n > 1 ? 10.0 * i / (n - 1) : 2.0);  // y = 0: a double root, ~20 iterations
   } else if (which == 1) {
     for (casadi_int i = 0; i < n; ++i) { in[0].push_back(U(0.5, 2.5)); in[0].push_back(U(0.5, 2.5)); in[1].push_back(U(-1, 1)); in[1].push_back(U(-1, 1)); }
+  } else if (which == 4 || which == 5) {
+    for (casadi_int i = 0; i < n; ++i) for (int k = 0; k < 4; ++k) { in[0].push_back(U(-1, 1)); in[1].push_back(U(-3, 3)); }
   } else {
     for (casadi_int i = 0; i < n; ++i) { in[0].push_back(U(-4, 4)); in[1].push_back(U(-3, 3)); }
   }
@@ -551,7 +562,7 @@ static std::vector<std::vector<double>> newton_inputs(int which, casadi_int n) {
 
 static void newton_lowering_checks() {
   const casadi_int n = 200;
-  for (int which = 0; which < 4; ++which) {
+  for (int which = 0; which < 6; ++which) {
     Function rf = newton_case(which);
     CHECK(CudaMap::is_newton(rf), rf.class_name());
     Function ref = rf.map(n, "serial");
