@@ -521,9 +521,24 @@ namespace casadi {
         std::vector<Vals> x_tape, v_tape;
         if (backward) x_tape.push_back(x);
         double t = I->t0_;
+        Vals u(nu, zero), u_raw_prev;
         for (casadi_int k = 0; k < nt; ++k) {
           const double t_next = I->tout_.at(k);
-          Vals u = take(INTEGRATOR_U, k * nu, nu);
+          // Integrator::eval passes new controls only where next_stop (:2566-2583) finds u[k-1] != u[k] in some entry, and
+          // otherwise keeps what it holds -- equal values, but possibly a zero of the other sign: a bit-exact select
+          const Vals u_raw = take(INTEGRATOR_U, k * nu, nu);
+          if (k == 0 || nu == 0 || !arg.at(INTEGRATOR_U)) {
+            u = u_raw;
+          } else {
+            ccu_int changed = zero;
+            for (casadi_int i = 0; i < nu; ++i) changed = op(OP_OR, changed, op(OP_NE, u_raw_prev[i], u_raw[i]));
+            for (casadi_int i = 0; i < nu; ++i) {
+              ccu_int h = lib.builder_select(b, changed, u_raw[i], u[i]);
+              casadi_assert(h >= 0, "Map 'cuda': " + std::string(lib.last_error()));
+              u[i] = h;
+            }
+          }
+          u_raw_prev = u_raw;
           const casadi_int nj = I->disc_.at(k + 1) - I->disc_.at(k);
           const double h = (t_next - t) / nj;
           for (casadi_int j = 0; j < nj; ++j) {

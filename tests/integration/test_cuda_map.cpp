@@ -425,6 +425,21 @@ static void integrator_lowering_checks() {
     auto in = integrator_inputs(ref, 31);
     check_bits(eval_tape(CudaMap::lowered_tape(I), n, in), eval(ref, in), "simplified rk integrator");
   }
+  // a control that repeats with the other zero sign: Integrator::eval keeps the control it holds while next_stop finds no
+  // change (-0. == +0.), which shows in the sign of a zero state
+  {
+    SX x = SX::sym("x"), u = SX::sym("u");
+    Function I = integrator("intg_zero", "rk", SXDict{{"x", x}, {"u", u}, {"ode", u}}, 0.0, std::vector<double>{0.5, 1.0, 1.5},
+                            Dict{{"number_of_finite_elements", 2}});
+    Function ref = I.map(4, "serial");
+    auto in = integrator_inputs(ref, 5);
+    in[INTEGRATOR_X0] = {-0.0, -0.0, -0.0, 1.0};
+    in[INTEGRATOR_U] = {-0.0, 0.0, -0.0,   0.0, -0.0, -0.0,   -0.0, -0.0, 0.0,   -0.0, 0.0, 0.5};
+    auto want = eval(ref, in);
+    CHECK(std::signbit(want[INTEGRATOR_XF][2]) && !std::signbit(want[INTEGRATOR_XF][3 + 2]),
+          "the reference keeps a -0 control across a +0 one (and a +0 one across a -0 one)");
+    check_bits(eval_tape(CudaMap::lowered_tape(I), 4, in), want, "rk integrator with controls that repeat with the other zero sign");
+  }
   // adjoint sensitivities: the adjoint integrator Integrator::get_reverse creates has backward states; its backward sweep
   // (impulses of the seeds at the output times, retreat through the forward sweep's tape) is replayed with the reference's
   // data-dependent shortcuts -- no impulse for an all-zero seed, no backward integration before the first impulse -- as
