@@ -1240,7 +1240,9 @@ namespace casadi {
     *n_failed = static_cast<casadi_int>(counts[3] + counts[0]);
     *n_singular = singular;
     if (flag) return flag;
-    return (P.error_on_fail && *n_failed > 0) || singular > 0 ? 1 : 0;
+    // (a singular Jacobian is not an error here: Newton::solve ignores the return value of Linsol::nfact, newton.cpp:173-174,
+    // and solves with whatever the factorisation holds -- the tapes do the same arithmetic; the count is informational)
+    return P.error_on_fail && *n_failed > 0 ? 1 : 0;
   }
 
   namespace {
@@ -1392,10 +1394,12 @@ namespace casadi {
         flag = newton_run(newton_plan_, n_*rep_, arg, res, be, &n_failed, &n_singular, launches);
       }
       m->fstats.at("cuda").toc();
-      // Rootfinder::eval raises when an instance failed and error_on_fail is set (rootfinder.cpp:294-296); a singular
-      // Jacobian makes Linsol::nfact fail (linsol_qr.cpp:146-163)
-      casadi_assert(n_singular == 0, "Map 'cuda': the Jacobian of rootfinder '" + leaf_.name() + "' is numerically singular for "
-                    + str(n_singular) + " instance(s)");
+      // Rootfinder::eval raises when an instance failed and error_on_fail is set (rootfinder.cpp:294-296).  A numerically
+      // singular Jacobian is not an error by itself: Newton::solve ignores the failure of Linsol::nfact (newton.cpp:173-174)
+      // and the step is whatever casadi_qr_solve makes of the factorisation -- reproduced bit for bit by the tapes
+      if (n_singular > 0 && verbose_)
+        casadi_message("Map 'cuda': the Jacobian of rootfinder '" + leaf_.name() + "' was numerically singular in "
+                       + str(n_singular) + " factorisation(s)");
       if (n_failed > 0 && newton_plan_.error_on_fail)
         casadi_error("rootfinder process failed for " + str(n_failed) + " of " + str(n_*rep_) + " instances of '" + leaf_.name()
                      + "'. Set 'error_on_fail' option to false to ignore this error.");

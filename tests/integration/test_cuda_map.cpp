@@ -532,11 +532,13 @@ struct OracleNewtonBackend : public CudaMap::NewtonBackend {
 // (1) a 2 x 2 system with a parameter and an auxiliary output, exact-class; (2) atan(x) = y/4 from far away (the line
 // search must damp the step); (3) as (0) without line search and with too few iterations, failures ignored
 static Function newton_case(int which) {
-  if (which == 0 || which == 3) {
+  if (which == 0 || which == 3 || which == 6) {
     MX x = MX::sym("x"), y = MX::sym("y");
     Function f("f", {x, y}, {x * x - y});
     Dict opts = {{"linear_solver", "qr"}};
     if (which == 3) { opts["line_search"] = false; opts["max_iter"] = 3; opts["error_on_fail"] = false; }
+    // 6: some instances start at x = 0, where the Jacobian 2x is singular: Newton::solve ignores the failed factorisation
+    if (which == 6) { opts["line_search"] = false; opts["max_iter"] = 30; opts["error_on_fail"] = false; }
     return rootfinder("finv" + str(which), "newton", f, opts);
   } else if (which == 1) {
     SX x = SX::sym("x", 2), p = SX::sym("p", 2);
@@ -562,8 +564,9 @@ static std::vector<std::vector<double>> newton_inputs(int which, casadi_int n) {
   std::vector<std::vector<double>> in(2);
   std::mt19937_64 g(97 + which);
   auto U = [&](double lo, double hi) { return lo + (hi - lo) * std::generate_canonical<double, 53>(g); };
-  if (which == 0 || which == 3) {
+  if (which == 0 || which == 3 || which == 6) {
     in[0].assign(n, 1.0);
+    if (which == 6) for (casadi_int i = 0; i < n; i += 9) in[0][i] = 0.0;
     for (casadi_int i = 0; i < n; ++i) in[1].push_back(n > 1 ? 10.0 * i / (n - 1) : 2.0);  // y = 0: a double root, ~20 iterations
   } else if (which == 1) {
     for (casadi_int i = 0; i < n; ++i) { in[0].push_back(U(0.5, 2.5)); in[0].push_back(U(0.5, 2.5)); in[1].push_back(U(-1, 1)); in[1].push_back(U(-1, 1)); }
@@ -577,7 +580,7 @@ static std::vector<std::vector<double>> newton_inputs(int which, casadi_int n) {
 
 static void newton_lowering_checks() {
   const casadi_int n = 200;
-  for (int which = 0; which < 6; ++which) {
+  for (int which = 0; which < 7; ++which) {
     Function rf = newton_case(which);
     CHECK(CudaMap::is_newton(rf), rf.class_name());
     Function ref = rf.map(n, "serial");
@@ -593,7 +596,9 @@ static void newton_lowering_checks() {
     casadi_int n_failed = -1, n_singular = -1, launches[2] = {0, 0};
     int flag = CudaMap::newton_run(P, n, arg.data(), res.data(), be, &n_failed, &n_singular, launches);
     CHECK(flag == 0, "newton_run flag " + str(flag));
-    CHECK(n_singular == 0, "singular " + str(n_singular));
+    CHECK(which == 6 ? n_singular > 0 : n_singular == 0, "singular " + str(n_singular));
+    // (case 6: the step through the singular factorisation is -inf, the next iterate NaN, and max|F| over NaNs is 0 under
+    // std::max: the reference "converges" to NaN, and so does the plan)
     CHECK(which == 3 ? n_failed > 0 : n_failed == 0, "failed instances: " + str(n_failed));
     check_bits(got, want, "Newton rootfinder case " + str(which));
     printf("newton case %d: tapes %zu + %zu instructions, %lld direction + %lld line-search launches, %lld failed, x[last] = %.17g\n", which,
