@@ -10,6 +10,7 @@
 #include <casadi/solvers/newton.hpp>  // option members of the Newton plugin class (layout only; nothing is linked)
 #include "mx_node.hpp"
 #include "solve.hpp"
+#include "switch.hpp"
 
 #include <dlfcn.h>
 
@@ -735,6 +736,70 @@ namespace casadi {
         }
       }
 
+      // casadi_project on handles: the nonzeros of pattern `to` taken from a matrix with pattern `from`, zero where absent
+      Vals project_vals(const Vals& v, const Sparsity& from, const Sparsity& to) {
+        if (from == to) return v;
+        casadi_assert(from.size() == to.size(), "Map 'cuda': projection between patterns of different dimension");
+        Vals r(to.nnz(), cst(0.));
+        const casadi_int *fc = from.colind(), *fr = from.row(), *tc = to.colind(), *tr = to.row();
+        for (casadi_int c = 0; c < to.size2(); ++c) {
+          casadi_int kf = fc[c];
+          for (casadi_int kt = tc[c]; kt < tc[c + 1]; ++kt) {
+            while (kf < fc[c + 1] && fr[kf] < tr[kt]) ++kf;
+            if (kf < fc[c + 1] && fr[kf] == tr[kt]) r[kt] = v.at(kf);
+          }
+        }
+        return r;
+      }
+
+      // Switch::eval (switch.cpp:153-211; Function::conditional / if_else): the reference evaluates the one case the index
+      // selects -- k = static_cast<casadi_int>(index), the default for k outside [0, n) -- with operands and results
+      // projected between the sparsity of the switch and of the case.  A thread of a map cannot branch per instance, so
+      // every case is evaluated and the results are merged with bit-exact selects on (trunc(index) == k).
+      void call_switch(const Function& f, const Switch* sw, const std::vector<const Vals*>& arg, std::vector<Vals*>& res) {
+        const casadi_int nf = static_cast<casadi_int>(sw->f_.size()), n_in = f.n_in(), n_out = f.n_out();
+        casadi_assert(!sw->f_def_.is_null(), "Map 'cuda': switch '" + f.name() + "' has no default case");
+        const ccu_int zero = cst(0.);
+        const ccu_int index = arg.at(0) && !arg[0]->empty() ? arg[0]->at(0) : zero;
+        auto sel = [&](ccu_int c, ccu_int a, ccu_int b2) {
+          ccu_int h = lib.builder_select(b, c, a, b2);
+          casadi_assert(h >= 0, "Map 'cuda': " + std::string(lib.last_error()));
+          return h;
+        };
+        // truncation toward zero of the conversion to an integer
+        const ccu_int trunc = sel(op(OP_LE, zero, index), op(OP_FLOOR, index), op(OP_CEIL, index));
+        auto eval_case = [&](const Function& fk, std::vector<Vals>& out) {
+          casadi_assert(!fk.is_null(), "Map 'cuda': switch '" + f.name() + "' has an empty case");
+          std::vector<Vals> a(n_in - 1), r(n_out);
+          std::vector<const Vals*> ap(n_in - 1, nullptr);
+          std::vector<Vals*> rp(n_out, nullptr);
+          for (casadi_int i = 0; i + 1 < n_in; ++i) {
+            if (!arg.at(i + 1)) continue;
+            a[i] = project_vals(*arg[i + 1], f.sparsity_in(i + 1), fk.sparsity_in(i));
+            ap[i] = &a[i];
+          }
+          for (casadi_int i = 0; i < n_out; ++i) {
+            if (!res.at(i)) continue;
+            r[i].assign(fk.nnz_out(i), zero);
+            rp[i] = &r[i];
+          }
+          call(fk, ap, rp);
+          out.resize(n_out);
+          for (casadi_int i = 0; i < n_out; ++i)
+            if (res[i]) out[i] = project_vals(r[i], fk.sparsity_out(i), f.sparsity_out(i));
+        };
+        std::vector<Vals> acc;
+        eval_case(sw->f_def_, acc);
+        for (casadi_int k = 0; k < nf; ++k) {
+          std::vector<Vals> rk;
+          eval_case(sw->f_[k], rk);
+          const ccu_int hit = op(OP_EQ, trunc, cst(static_cast<double>(k)));
+          for (casadi_int i = 0; i < n_out; ++i)
+            if (res[i]) for (size_t e = 0; e < acc[i].size(); ++e) acc[i][e] = sel(hit, rk[i][e], acc[i][e]);
+        }
+        for (casadi_int i = 0; i < n_out; ++i) if (res[i]) *res[i] = acc[i];
+      }
+
       void call(const Function& f, const std::vector<const Vals*>& arg, std::vector<Vals*>& res) {
         if (f.is_a("SXFunction")) {
           call_sx(f, arg, res);
@@ -748,6 +813,8 @@ namespace casadi {
           Dict inf = f.info();
           call_repeated(inf.at("f").to_function(), inf.at("n").to_int(), std::vector<bool>(f.n_in(), false),
                         std::vector<bool>(f.n_out(), false), arg, res);
+        } else if (auto* sw = dynamic_cast<const Switch*>(f.get())) {
+          call_switch(f, sw, arg, res);
         } else if (auto* ms = dynamic_cast<const MapSum*>(f.get())) {
           // MapSum::eval_gen (mapsum.cpp:154-186): reduced inputs are shared, reduced outputs are cleared and then
           // accumulated instance by instance, in index order (casadi_add: y += x)

@@ -269,6 +269,34 @@ static void mx_vocabulary_checks() {
     std::vector<MX> rs = Gs(std::vector<MX>{reshape(x, 2, 3), b(3)});
     check("maps", {K, b}, {r.at(0), r.at(1), rs.at(0), rs.at(1), rr.at(0), rr.at(1)}, 45);
   }
+  // a conditional (Function::conditional -> Switch, switch.cpp:153-211) next to the solve: the reference evaluates the one
+  // case the index selects, the lowering all of them, merged by selects on trunc(index) == k; cases with their own patterns
+  {
+    SX p = SX::sym("p", 6), q = SX::sym("q", 6), ps = SX::sym("ps", Sparsity::diag(3));
+    Function f0("f0", {p, q}, {p * q - 1, dot(p, q)});
+    Function f1("f1", {p, q}, {p / (q * q + 1), sum1(p) * sum1(q)});
+    Function fd("fd", {p, q}, {-p, SX(1, 1)});                     // (a structurally empty second result: projected)
+    Function sw = Function::conditional("sw", {f0, f1}, fd);
+    MX ind = MX::sym("ind");
+    std::vector<MX> r = sw(std::vector<MX>{ind, x, b});
+    Function f = check("switch", {K, b, ind}, {r.at(0), r.at(1) + x(0)}, 48);
+    // the index values that matter: each case, beyond both ends, and fractions that truncate toward zero
+    Function ref = f.map(n, "serial");
+    auto vin = kkt_like_inputs(ref, n, 49);
+    const double idx[] = {0, 1, 2, -1, 0.7, 1.9, -0.5, -0.0, 1e9, -3.2, 1.0000001, 0.999999};
+    for (casadi_int i = 0; i < n; ++i) vin[2][i] = idx[i % 12];
+    check_bits(eval_tape(CudaMap::lowered_tape(f), n, vin), eval(ref, vin), "MX vocabulary: switch with chosen index values");
+    for (const Function& d : {f.forward(1), f.reverse(1)}) {
+      Function dref = d.map(n, "serial");
+      auto din = kkt_like_inputs(dref, n, 50);
+      for (casadi_int i = 0; i < n; ++i) din[2][i] = idx[i % 12];
+      try {
+        check_bits(eval_tape(CudaMap::lowered_tape(d), n, din), eval(dref, din), "MX vocabulary: " + d.name());
+      } catch (std::exception& e) {
+        CHECK(false, "MX vocabulary: " + d.name() + " was refused: " + e.what());
+      }
+    }
+  }
   // still refused, loudly: nodes without a numeric evaluation in the reference, side effects
   {
     bool threw = false;
