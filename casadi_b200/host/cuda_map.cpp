@@ -7,6 +7,7 @@
 #include "mapsum.hpp"
 #include "multiplication.hpp"
 #include "rootfinder_impl.hpp"
+#include <casadi/solvers/linear_interpolant.hpp>  // data members of the lookup-table plugin (layout only; nothing is linked)
 #include <casadi/solvers/newton.hpp>  // option members of the Newton plugin class (layout only; nothing is linked)
 #include "mx_node.hpp"
 #include "solve.hpp"
@@ -736,6 +737,128 @@ namespace casadi {
         }
       }
 
+      // A lookup table (interpolant(..., "linear", grid, values): casadi/solvers/linear_interpolant.cpp:85-96, 142-152) and its
+      // Jacobian: casadi_interpn / casadi_interpn_grad (runtime/) replayed with their own operation order.  The left index
+      // of every dimension (casadi_low) is data, and a tape has no indexed loads, so the grid points and the table entries a
+      // lookup touches are gathered by bit-exact selects on one-hot flags "the index is j" -- comparisons of x with the
+      // (constant) grid.  Cost: about a select per table entry and corner, so only tables of moderate size are accepted.
+      void call_interpolant(const Function& f, const LinearInterpolant* I, bool grad, const std::vector<const Vals*>& arg,
+                            std::vector<Vals*>& res) {
+        const std::string who = "Map 'cuda': interpolant '" + f.name() + "': ";
+        casadi_assert(!I->has_parametric_values() && !I->has_parametric_grid(), who + "parametric grids / values have no device lowering");
+        casadi_assert(I->batch_x_ == 1, who + "batch_x > 1 has no device lowering");
+        const casadi_int ndim = I->ndim_, m = I->m_;
+        const std::vector<double>& grid = I->grid_;
+        const std::vector<double>& values = I->values_;
+        const std::vector<casadi_int>& offset = I->offset_;
+        double work = static_cast<double>(m) * (1 << ndim);
+        for (casadi_int i = 0; i < ndim; ++i) work *= static_cast<double>(offset[i + 1] - offset[i]);
+        casadi_assert(work <= 2e5, who + "the table is too large to be gathered by selects on the device (" + str(work) + " selects per lookup)");
+        if (!res.at(0)) return;
+        const ccu_int zero = cst(0.), one = cst(1.);
+        auto sel = [&](ccu_int c, ccu_int a, ccu_int b2) {
+          ccu_int h = lib.builder_select(b, c, a, b2);
+          casadi_assert(h >= 0, "Map 'cuda': " + std::string(lib.last_error()));
+          return h;
+        };
+        // casadi_interpn_weights: per dimension the one-hot flags of the left index j, alpha = (x - g[j]) / (g[j+1] - g[j])
+        std::vector<std::vector<ccu_int>> hit(ndim);
+        Vals alpha(ndim), delta(ndim);
+        for (casadi_int i = 0; i < ndim; ++i) {
+          const ccu_int xi = arg.at(0) ? arg[0]->at(i) : zero;
+          const double* g = grid.data() + offset[i];
+          const casadi_int ng = offset[i + 1] - offset[i];
+          casadi_assert(ng >= 2, who + "a grid needs two points");
+          hit[i].assign(ng - 1, zero);
+          if (I->lookup_mode_.at(i) == 1) {
+            // "exact": j = (casadi_int)((x - g0)*(ng-1)/dg) clamped to [0, ng-2]; trunc(t) >= k  <=>  t >= k for k >= 1
+            const ccu_int t = op(OP_DIV, op(OP_MUL, op(OP_SUB, xi, cst(g[0])), cst(static_cast<double>(ng - 1))), cst(g[ng - 1] - g[0]));
+            std::vector<ccu_int> ge(ng, zero);  // ge[k] = (t >= k), k = 1 .. ng-2
+            for (casadi_int k = 1; k <= ng - 2; ++k) ge[k] = op(OP_LE, cst(static_cast<double>(k)), t);
+            for (casadi_int j = 0; j <= ng - 2; ++j) {
+              const ccu_int lo = j == 0 ? one : ge[j], hi = j == ng - 2 ? zero : ge[j + 1];
+              hit[i][j] = op(OP_AND, lo, op(OP_NOT, hi));
+            }
+          } else {
+            // linear / binary search over a strictly increasing grid: the first j in [0, ng-2) with x < g[j+1], else ng-2
+            std::vector<ccu_int> lt(ng, zero);  // lt[k] = (x < g[k]), k = 1 .. ng-2
+            for (casadi_int k = 1; k <= ng - 2; ++k) lt[k] = op(OP_LT, xi, cst(g[k]));
+            for (casadi_int j = 0; j <= ng - 2; ++j) {
+              const ccu_int below = j == ng - 2 ? one : lt[j + 1], not_earlier = j == 0 ? one : op(OP_NOT, lt[j]);
+              hit[i][j] = op(OP_AND, below, not_earlier);
+            }
+          }
+          ccu_int gj = cst(g[ng - 2]), gj1 = cst(g[ng - 1]);
+          for (casadi_int j = ng - 2; j-- > 0; ) { gj = sel(hit[i][j], cst(g[j]), gj); gj1 = sel(hit[i][j], cst(g[j + 1]), gj1); }
+          delta[i] = op(OP_SUB, gj1, gj);
+          alpha[i] = op(OP_DIV, op(OP_SUB, xi, gj), delta[i]);
+        }
+        // the table entry values[(index + corner) . strides * m + k], gathered dimension by dimension
+        std::vector<casadi_int> ngs(ndim), stride(ndim);
+        for (casadi_int i = 0, ld = 1; i < ndim; ++i) { ngs[i] = offset[i + 1] - offset[i]; stride[i] = ld; ld *= ngs[i]; }
+        auto gather = [&](const std::vector<casadi_int>& corner, casadi_int k) {
+          // level d holds, for every multi-index of the dimensions >= d, the entry selected in the dimensions < d
+          std::vector<ccu_int> cur(static_cast<size_t>(stride[ndim - 1] * ngs[ndim - 1]));
+          for (size_t e = 0; e < cur.size(); ++e) cur[e] = cst(values.at(e * m + k));
+          casadi_int inner = 1;  // entries per block of the dimensions already resolved (always 1 after resolution)
+          casadi_int count = static_cast<casadi_int>(cur.size());
+          for (casadi_int d = 0; d < ndim; ++d) {
+            const casadi_int ng = ngs[d], blocks = count / ng;
+            std::vector<ccu_int> next(static_cast<size_t>(blocks));
+            for (casadi_int bl = 0; bl < blocks; ++bl) {
+              // entries bl*ng + (j + corner[d]), j = 0 .. ng-2
+              ccu_int v = cur[static_cast<size_t>(bl * ng + (ng - 2) + corner[d])];
+              for (casadi_int j = ng - 2; j-- > 0; ) v = sel(hit[d][j], cur[static_cast<size_t>(bl * ng + j + corner[d])], v);
+              next[static_cast<size_t>(bl)] = v;
+            }
+            cur.swap(next);
+            count = blocks;
+          }
+          (void)inner;
+          return cur.at(0);
+        };
+        std::vector<casadi_int> corner(ndim, 0);
+        auto flip = [&]() {  // casadi_flip
+          for (casadi_int i = 0; i < ndim; ++i) { if (corner[i]) corner[i] = 0; else { corner[i] = 1; return true; } }
+          return false;
+        };
+        if (!grad) {
+          // casadi_interpn: res = 0; per corner res[k] += c * value, c = prod_i (corner_i ? alpha_i : 1 - alpha_i) from c = 1
+          Vals r(m, zero);
+          do {
+            ccu_int c = one;
+            for (casadi_int i = 0; i < ndim; ++i) c = op(OP_MUL, c, corner[i] ? alpha[i] : op(OP_SUB, one, alpha[i]));
+            for (casadi_int k = 0; k < m; ++k) r[k] = op(OP_ADD, r[k], op(OP_MUL, c, gather(corner, k)));
+          } while (flip());
+          *res[0] = r;
+        } else {
+          // casadi_interpn_grad: per corner v = value (coeff[i] = the partial product before dimension i), then from the last
+          // dimension down grad[i] +/-= v * coeff[i], v *= (alpha_i | 1 - alpha_i); finally grad[i] /= g[j+1] - g[j]
+          Vals gr(ndim * m, zero);
+          do {
+            Vals coeff(ndim);
+            ccu_int c = one;
+            for (casadi_int i = 0; i < ndim; ++i) {
+              coeff[i] = c;
+              c = op(OP_MUL, c, corner[i] ? alpha[i] : op(OP_SUB, one, alpha[i]));
+            }
+            Vals v(m);
+            for (casadi_int k = 0; k < m; ++k) v[k] = op(OP_ADD, zero, gather(corner, k));  // (casadi_clear(v); v[k] += values[k])
+            for (casadi_int i = ndim; i-- > 0; ) {
+              for (casadi_int k = 0; k < m; ++k) {
+                const ccu_int term = op(OP_MUL, v[k], coeff[i]);
+                gr[i * m + k] = corner[i] ? op(OP_ADD, gr[i * m + k], term) : op(OP_SUB, gr[i * m + k], term);
+                v[k] = op(OP_MUL, v[k], corner[i] ? alpha[i] : op(OP_SUB, one, alpha[i]));
+              }
+            }
+          } while (flip());
+          for (casadi_int i = 0; i < ndim; ++i)
+            for (casadi_int k = 0; k < m; ++k) gr[i * m + k] = op(OP_DIV, gr[i * m + k], delta[i]);
+          casadi_assert(static_cast<casadi_int>(res[0]->size()) == ndim * m, who + "unexpected Jacobian size");
+          *res[0] = gr;
+        }
+      }
+
       // casadi_project on handles: the nonzeros of pattern `to` taken from a matrix with pattern `from`, zero where absent
       Vals project_vals(const Vals& v, const Sparsity& from, const Sparsity& to) {
         if (from == to) return v;
@@ -815,6 +938,12 @@ namespace casadi {
                         std::vector<bool>(f.n_out(), false), arg, res);
         } else if (auto* sw = dynamic_cast<const Switch*>(f.get())) {
           call_switch(f, sw, arg, res);
+        } else if (f.class_name() == "LinearInterpolant") {
+          call_interpolant(f, static_cast<const LinearInterpolant*>(f.get()), false, arg, res);
+        } else if (f.class_name() == "LinearInterpolantJac") {
+          const Function& of = f->derivative_of_;
+          casadi_assert(!of.is_null() && of.class_name() == "LinearInterpolant", "Map 'cuda': '" + f.name() + "' has no interpolant");
+          call_interpolant(f, static_cast<const LinearInterpolant*>(of.get()), true, arg, res);
         } else if (auto* ms = dynamic_cast<const MapSum*>(f.get())) {
           // MapSum::eval_gen (mapsum.cpp:154-186): reduced inputs are shared, reduced outputs are cleared and then
           // accumulated instance by instance, in index order (casadi_add: y += x)

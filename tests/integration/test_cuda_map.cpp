@@ -297,6 +297,54 @@ static void mx_vocabulary_checks() {
       }
     }
   }
+  // lookup tables: interpolant(..., "linear", ...) has no eval_sx, so a function that calls one is lowered; the table
+  // entries of a lookup are gathered by selects on the one-hot left index.  1-D and 2-D tables, two values per grid point,
+  // the three lookup modes, points inside, on grid points and outside the grid, and the derivative functions
+  {
+    std::vector<double> g1 = {-1, -0.5, 0, 0.25, 0.75, 1.5, 2}, v1;
+    for (size_t i = 0; i < g1.size(); ++i) v1.push_back(std::sin(3 * g1[i]) + 0.1 * static_cast<double>(i));
+    std::vector<std::vector<double>> g2 = {{0, 0.5, 1, 2, 4}, {-1, 0, 1, 3}};
+    std::vector<double> v2;
+    for (size_t j = 0; j < g2[1].size(); ++j)
+      for (size_t i = 0; i < g2[0].size(); ++i)
+        for (int k = 0; k < 2; ++k) v2.push_back(std::cos(g2[0][i] + 2 * g2[1][j]) * (k + 1) - 0.3 * static_cast<double>(i * j));
+    std::vector<double> gu = {0, 0.5, 1, 1.5, 2, 2.5};
+    std::vector<double> vu = {1, -2, 0.5, 3, -0.0, 2};
+    int cases = 0;
+    for (int which = 0; which < 4; ++which) {
+      Function L1 = interpolant("lut1", "linear", {g1}, v1, which == 1 ? Dict{{"lookup_mode", std::vector<std::string>{"binary"}}} : Dict());
+      Function L2 = interpolant("lut2", "linear", g2, v2, which == 2 ? Dict{{"lookup_mode", std::vector<std::string>{"binary", "linear"}}} : Dict());
+      Function Lu = interpolant("lutu", "linear", {gu}, vu, which == 3 ? Dict{{"lookup_mode", std::vector<std::string>{"exact"}}} : Dict());
+      MX a = MX::sym("a"), c = MX::sym("c", 2);
+      MX y1 = L1(std::vector<MX>{a}).at(0), y2 = L2(std::vector<MX>{c}).at(0), yu = Lu(std::vector<MX>{2 * a + 1}).at(0);
+      Function f("lut_case" + str(which), {a, c}, {y1 * y2(0) + yu, y2 + a, sin(y1)});
+      // (Function::expand "succeeds" on it, with the interpolant left as a call inside the SX function: not an expansion)
+      bool holds_call = false;
+      try {
+        Function e = f.expand();
+        for (casadi_int k = 0; k < e.n_instructions(); ++k) holds_call = holds_call || e.instruction_id(k) == OP_CALL;
+      } catch (std::exception&) { holds_call = true; }
+      CHECK(holds_call, "a function with a lookup table must not expand to a pure SX tape (otherwise it does not test the lowering)");
+      std::vector<Function> fs = {f, f.forward(1), f.reverse(1), f.jacobian()};
+      for (const Function& d : fs) {
+        const casadi_int nn = 40;
+        Function ref = d.map(nn, "serial");
+        auto vin = random_inputs(ref, 71 + which, -1.5, 2.5);
+        // the first operand on grid points, on the ends and beyond them
+        const double special[] = {-1, -0.5, 0, 0.25, 2, -1.25, 2.5, 0.75, 1.5, -0.0};
+        for (casadi_int i = 0; i < 10; ++i) vin[0][i] = special[i];
+        const double special2[] = {0, -1, 0.5, 0, 4, 3, 5, 4, -1, -2, 2, 1};
+        for (casadi_int i = 0; i < 12; ++i) vin[1][20 + i] = special2[i];
+        try {
+          check_bits(eval_tape(CudaMap::lowered_tape(d), nn, vin), eval(ref, vin), "lookup tables, case " + str(which) + ": " + d.name());
+          ++cases;
+        } catch (std::exception& e) {
+          CHECK(false, "lookup tables, case " + str(which) + ": " + d.name() + " was refused: " + e.what());
+        }
+      }
+    }
+    printf("lookup tables (linear interpolants, three lookup modes) and their derivative functions: %d functions lowered\n", cases);
+  }
   // still refused, loudly: nodes without a numeric evaluation in the reference, side effects
   {
     bool threw = false;
