@@ -2,11 +2,13 @@
  * CudaMap -- see cuda_map.hpp.  New file for casadi/core/.
  */
 #include "cuda_map.hpp"
+#include "bspline.hpp"
 #include "integrator_impl.hpp"
 #include "linsol.hpp"
 #include "mapsum.hpp"
 #include "multiplication.hpp"
 #include "rootfinder_impl.hpp"
+#include <casadi/solvers/bspline_interpolant.hpp>  // S_ of the B-spline interpolant (layout only)
 #include <casadi/solvers/linear_interpolant.hpp>  // data members of the lookup-table plugin (layout only; nothing is linked)
 #include <casadi/solvers/newton.hpp>  // option members of the Newton plugin class (layout only; nothing is linked)
 #include "mx_node.hpp"
@@ -18,6 +20,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <map>
 #include <mutex>
@@ -386,6 +389,13 @@ namespace casadi {
             Vals r(a.size());
             for (size_t e = 0; e < a.size(); ++e) r[e] = op(static_cast<int>(o), a[e]);
             w[out.at(0)] = r;
+          } else if (o == OP_BSPLINE) {
+            const BSplineCommon* bs = dynamic_cast<const BSplineCommon*>(x.get());
+            casadi_assert(bs != nullptr, "Map 'cuda': " + x.class_name() + " is not a B-spline node");
+            const BSpline* bc = dynamic_cast<const BSpline*>(x.get());
+            Vals coeffs;
+            if (bc) { for (double v : bc->coeffs_) coeffs.push_back(cst(v)); } else { coeffs = W(in.at(1)); }
+            w[out.at(0)] = bspline_eval(f, bs, W(in.at(0)), coeffs);
           } else if (o == OP_DOT || o == OP_NORMF || o == OP_NORM1 || o == OP_NORMINF) {
             // casadi_dot / casadi_norm_2 / casadi_norm_1 / casadi_norm_inf (runtime/): the accumulator starts from an
             // explicit zero, as in the numeric evaluation (0 + (-0) is +0; an SX expansion would drop the addition)
@@ -412,7 +422,7 @@ namespace casadi {
             w[out.at(0)] = Vals(1, r);
           } else if (o == OP_TRANSPOSE || o == OP_PROJECT || o == OP_RANK1
                      || o == OP_SETNONZEROS || o == OP_ADDNONZEROS || o == OP_MMIN || o == OP_MMAX || o == OP_SPARSITY_CAST
-                     || o == OP_LIFT) {
+                     || o == OP_LIFT || o == OP_EINSTEIN) {
             node_sx(f, x, in, out, w);
           } else {
             casadi_error("Map 'cuda': MX operation '" + x.class_name() + "' (op " + str(o) + ") in function '" + f.name()
@@ -737,6 +747,134 @@ namespace casadi {
         }
       }
 
+      // A B-spline node (MX::bspline, interpolant(..., "bspline", ...); BSpline::eval / BSplineParametric::eval, bspline.cpp:437-455):
+      // casadi_nd_boor_eval (runtime/) replayed -- per dimension the knot span L (casadi_low), start = min(L, n_b-degree-1),
+      // the initial basis vector from the comparisons of x with the knots, casadi_de_boor over the 2*degree+2 knots from
+      // `start`, then casadi_tensor_ttv over the coefficients from `starts`.  Everything indexed by L or start is gathered
+      // by bit-exact selects on one-hot flags; the `if (bottom)` guards of de Boor's recursion (repeated knots) are
+      // selects on bottom != 0.
+      Vals bspline_eval(const Function& f, const BSplineCommon* bs, const Vals& xin, const Vals& coeffs) {
+        const std::string who = "Map 'cuda': B-spline in '" + f.name() + "': ";
+        const casadi_int nd = static_cast<casadi_int>(bs->degree_.size()), m = bs->m_;
+        casadi_assert(static_cast<casadi_int>(xin.size()) == nd, who + "unexpected argument size (batched evaluation has no device lowering)");
+        const ccu_int zero = cst(0.), one = cst(1.);
+        auto sel = [&](ccu_int c, ccu_int a, ccu_int b2) {
+          ccu_int h = lib.builder_select(b, c, a, b2);
+          casadi_assert(h >= 0, "Map 'cuda': " + std::string(lib.last_error()));
+          return h;
+        };
+        double work = static_cast<double>(m);
+        std::vector<std::vector<ccu_int>> start_hit(nd);  // one-hot flags of `start` per dimension
+        std::vector<Vals> boor(nd);                        // the degree+1 basis values per dimension
+        for (casadi_int k = 0; k < nd; ++k) {
+          const casadi_int degree = bs->degree_[k], n_knots = bs->offset_[k + 1] - bs->offset_[k], n_b = n_knots - degree - 1;
+          const double* knots = bs->knots_.data() + bs->offset_[k];
+          const ccu_int xk = xin[k];
+          // L = casadi_low(x, knots + degree, n_knots - 2*degree, mode): one-hot over 0 .. ng-2
+          const double* g = knots + degree;
+          const casadi_int ng = n_knots - 2 * degree;
+          casadi_assert(ng >= 2, who + "too few knots");
+          std::vector<ccu_int> L_hit(ng - 1, zero);
+          if (bs->lookup_mode_.at(k) == 1) {
+            const ccu_int t = op(OP_DIV, op(OP_MUL, op(OP_SUB, xk, cst(g[0])), cst(static_cast<double>(ng - 1))), cst(g[ng - 1] - g[0]));
+            std::vector<ccu_int> ge(ng, zero);
+            for (casadi_int j = 1; j <= ng - 2; ++j) ge[j] = op(OP_LE, cst(static_cast<double>(j)), t);
+            for (casadi_int j = 0; j <= ng - 2; ++j)
+              L_hit[j] = op(OP_AND, j == 0 ? one : ge[j], op(OP_NOT, j == ng - 2 ? zero : ge[j + 1]));
+          } else if (bs->lookup_mode_.at(k) == 2) {
+            // binary search (casadi_low case 2): x < g[1] -> 0, x > g[ng-1] -> ng-2, else the bisection -- on a
+            // non-decreasing grid with possibly repeated points it ends at the LAST j with g[j] <= x
+            std::vector<ccu_int> lt(ng, zero);
+            for (casadi_int j = 1; j <= ng - 1; ++j) lt[j] = op(OP_LT, xk, cst(g[j]));
+            for (casadi_int j = 0; j <= ng - 2; ++j)
+              L_hit[j] = op(OP_AND, j == ng - 2 ? one : lt[j + 1], j == 0 ? one : op(OP_NOT, lt[j]));
+          } else {
+            std::vector<ccu_int> lt(ng, zero);
+            for (casadi_int j = 1; j <= ng - 2; ++j) lt[j] = op(OP_LT, xk, cst(g[j]));
+            for (casadi_int j = 0; j <= ng - 2; ++j)
+              L_hit[j] = op(OP_AND, j == ng - 2 ? one : lt[j + 1], j == 0 ? one : op(OP_NOT, lt[j]));
+          }
+          // start = min(L, n_b - degree - 1): the flags of L folded onto 0 .. smax
+          const casadi_int smax = n_b - degree - 1;
+          casadi_assert(smax >= 0, who + "too few knots for the degree");
+          start_hit[k].assign(smax + 1, zero);
+          for (casadi_int j = 0; j <= ng - 2; ++j) {
+            const casadi_int sidx = std::min(j, smax);
+            start_hit[k][sidx] = start_hit[k][sidx] == zero ? L_hit[j] : op(OP_OR, start_hit[k][sidx], L_hit[j]);
+          }
+          auto gather_L = [&](casadi_int shift) {  // knots[L + shift]
+            ccu_int v = cst(knots[(ng - 2) + shift]);
+            for (casadi_int j = ng - 2; j-- > 0; ) v = sel(L_hit[j], cst(knots[j + shift]), v);
+            return v;
+          };
+          auto gather_start = [&](casadi_int shift) {  // knots[start + shift]
+            ccu_int v = cst(knots[smax + shift]);
+            for (casadi_int j = smax; j-- > 0; ) v = sel(start_hit[k][j], cst(knots[j + shift]), v);
+            return v;
+          };
+          // initial basis (nd_boor_eval): zeros; inside [knots[0], knots[end]]: x == knots[1] -> the first degree+1 ones,
+          // else x == knots[end] -> boor[degree], else knots[L+degree] == x -> boor[degree-1], else boor[degree]
+          Vals bo(2 * degree + 1, zero);
+          {
+            const ccu_int inside = op(OP_AND, op(OP_LE, cst(knots[0]), xk), op(OP_LE, xk, cst(knots[n_knots - 1])));
+            const ccu_int c1 = op(OP_EQ, xk, cst(knots[1])), c2 = op(OP_EQ, xk, cst(knots[n_knots - 1]));
+            const ccu_int c3 = op(OP_EQ, gather_L(degree), xk);
+            const ccu_int n1 = op(OP_NOT, c1), n2 = op(OP_NOT, c2), n3 = op(OP_NOT, c3);
+            const ccu_int only2 = op(OP_AND, n1, c2), only3 = op(OP_AND, op(OP_AND, n1, n2), c3), none = op(OP_AND, op(OP_AND, n1, n2), n3);
+            for (casadi_int i = 0; i <= degree; ++i) {
+              ccu_int v = c1;  // casadi_fill(boor, degree+1, 1.0)
+              if (i == degree) v = op(OP_OR, v, op(OP_OR, only2, none));
+              if (i == degree - 1) v = op(OP_OR, v, only3);
+              bo[i] = op(OP_AND, inside, v);
+            }
+          }
+          // casadi_de_boor(x, knots + start, 2*degree+2, degree, boor)
+          const casadi_int nk = 2 * degree + 2;
+          Vals kn(nk);
+          for (casadi_int i = 0; i < nk; ++i) kn[i] = gather_start(i);
+          for (casadi_int d = 1; d < degree + 1; ++d) {
+            for (casadi_int i = 0; i < nk - d - 1; ++i) {
+              ccu_int bv = zero;
+              const ccu_int bottom = op(OP_SUB, kn[i + d], kn[i]);
+              bv = sel(op(OP_NE, bottom, zero), op(OP_DIV, op(OP_MUL, op(OP_SUB, xk, kn[i]), bo[i]), bottom), bv);
+              const ccu_int bottom2 = op(OP_SUB, kn[i + d + 1], kn[i + 1]);
+              bv = sel(op(OP_NE, bottom2, zero),
+                       op(OP_ADD, bv, op(OP_DIV, op(OP_MUL, op(OP_SUB, kn[i + d + 1], xk), bo[i + 1]), bottom2)), bv);
+              bo[i] = bv;
+            }
+          }
+          boor[k] = Vals(bo.begin(), bo.begin() + degree + 1);
+          work *= static_cast<double>(degree + 1) * static_cast<double>(smax + 1);
+        }
+        casadi_assert(work <= 2e5, who + "the coefficient tensor is too large to be gathered by selects on the device ("
+                      + str(work) + " selects per evaluation)");
+        // casadi_tensor_ttv(ret, nd-1, nd, all_boor, boor_offset, starts, strides, c, m, 1.0, 0) on ret = 0
+        Vals ret(m, zero);
+        // coefficient c[off + j] with off = sum_k (start_k + i_k) * strides[k]: gathered over the one-hot starts, outer dimension first
+        std::vector<casadi_int> idx(nd, 0);
+        std::function<ccu_int(casadi_int, casadi_int, casadi_int)> gather = [&](casadi_int dim, casadi_int off, casadi_int j) -> ccu_int {
+          if (dim < 0) return coeffs.at(off + j);
+          const casadi_int smax = static_cast<casadi_int>(start_hit[dim].size()) - 1;
+          ccu_int v = gather(dim - 1, off + (smax + idx[dim]) * bs->strides_[dim], j);
+          for (casadi_int s2 = smax; s2-- > 0; ) v = sel(start_hit[dim][s2], gather(dim - 1, off + (s2 + idx[dim]) * bs->strides_[dim], j), v);
+          return v;
+        };
+        std::function<void(casadi_int, ccu_int)> ttv = [&](casadi_int dim, ccu_int weight) {
+          const casadi_int n_w = static_cast<casadi_int>(boor[dim].size());
+          for (casadi_int i = 0; i < n_w; ++i) {
+            idx[dim] = i;
+            const ccu_int ww = op(OP_MUL, weight, boor[dim][i]);
+            if (dim == 0) {
+              for (casadi_int j = 0; j < m; ++j) ret[j] = op(OP_ADD, ret[j], op(OP_MUL, ww, gather(nd - 1, 0, j)));
+            } else {
+              ttv(dim - 1, ww);
+            }
+          }
+        };
+        ttv(nd - 1, one);
+        return ret;
+      }
+
       // A lookup table (interpolant(..., "linear", grid, values): casadi/solvers/linear_interpolant.cpp:85-96, 142-152) and its
       // Jacobian: casadi_interpn / casadi_interpn_grad (runtime/) replayed with their own operation order.  The left index
       // of every dimension (casadi_low) is data, and a tape has no indexed loads, so the grid points and the table entries a
@@ -938,6 +1076,9 @@ namespace casadi {
                         std::vector<bool>(f.n_out(), false), arg, res);
         } else if (auto* sw = dynamic_cast<const Switch*>(f.get())) {
           call_switch(f, sw, arg, res);
+        } else if (f.class_name() == "BSplineInterpolant") {
+          // BSplineInterpolant::eval (casadi/solvers/bspline_interpolant.cpp:185-190) evaluates its MX function S_, one B-spline node
+          call(static_cast<const BSplineInterpolant*>(f.get())->S_, arg, res);
         } else if (f.class_name() == "LinearInterpolant") {
           call_interpolant(f, static_cast<const LinearInterpolant*>(f.get()), false, arg, res);
         } else if (f.class_name() == "LinearInterpolantJac") {

@@ -58,7 +58,9 @@ PLUGINS = {
     "linsol_ldl": ("linsol_ldl.cpp", "linsol_ldl_meta.cpp"),
     "linsol_qr": ("linsol_qr.cpp", "linsol_qr_meta.cpp"),
     "linsol_tridiag": ("linsol_tridiag.cpp", "linsol_tridiag_meta.cpp"),
+    "linsol_lsqr": ("lsqr.cpp", "lsqr_meta.cpp"),   # (BSplineInterpolant::init fits its coefficients with it)
     "interpolant_linear": ("linear_interpolant.cpp", "linear_interpolant_meta.cpp"),
+    "interpolant_bspline": ("bspline_interpolant.cpp", "bspline_interpolant_meta.cpp"),
     "integrator_rk": ("runge_kutta.cpp", "runge_kutta_meta.cpp"),
     "rootfinder_newton": ("newton.cpp", "newton_meta.cpp"),
 }
@@ -127,7 +129,7 @@ def generate_headers():
         "git_describe": "3.7.2", "feature_list": "\\n * dynamic-loading\\n * openmp\\n * thread",
         "CMAKE_BUILD_TYPE": "Release", "CMAKE_CXX_COMPILER_ID": "GNU",
         "CASADI_CMAKE_CXX_COMPILER": CXX, "CASADI_MODULES": "casadi;" + ";".join("casadi_" + p for p in PLUGINS),
-        "CASADI_PLUGINS": "Linsol::ldl;Linsol::qr;Linsol::tridiag;Interpolant::linear;Integrator::rk;Rootfinder::newton", "CASADI_INSTALL_PREFIX": os.path.join(OUT),
+        "CASADI_PLUGINS": "Linsol::ldl;Linsol::qr;Linsol::tridiag;Linsol::lsqr;Interpolant::linear;Interpolant::bspline;Integrator::rk;Rootfinder::newton", "CASADI_INSTALL_PREFIX": os.path.join(OUT),
         "CMAKE_SHARED_LIBRARY_PREFIX": "lib", "CMAKE_SHARED_LIBRARY_SUFFIX": ".so",
         "CMAKE_C_OUTPUT_EXTENSION": ".o", "casadi_lapack_libraries": "",
     }

@@ -345,6 +345,61 @@ static void mx_vocabulary_checks() {
     }
     printf("lookup tables (linear interpolants, three lookup modes) and their derivative functions: %d functions lowered\n", cases);
   }
+  // B-splines: interpolant(..., "bspline", ...) and MX::bspline nodes (constant and parametric coefficients) -- de Boor's
+  // recursion over knots gathered by selects; points inside, on knots, on the ends and outside, and the derivative functions
+  {
+    std::vector<double> g1 = {-1, -0.5, 0, 0.25, 0.75, 1.5, 2}, v1;
+    for (size_t i = 0; i < g1.size(); ++i) v1.push_back(std::sin(3 * g1[i]) + 0.1 * static_cast<double>(i));
+    std::vector<std::vector<double>> g2 = {{0, 0.5, 1, 2, 4}, {-1, 0, 1, 3, 3.5}};
+    std::vector<double> v2;
+    for (size_t j = 0; j < g2[1].size(); ++j)
+      for (size_t i = 0; i < g2[0].size(); ++i)
+        for (int k = 0; k < 2; ++k) v2.push_back(std::cos(g2[0][i] + 2 * g2[1][j]) * (k + 1) - 0.3 * static_cast<double>(i * j));
+    int cases = 0;
+    for (int which = 0; which < 3; ++which) {
+      MX a = MX::sym("a"), c = MX::sym("c", 2), cf = MX::sym("cf", 5);
+      std::vector<MX> outs;
+      std::vector<MX> ins = {a, c};
+      if (which == 0) {
+        Function B1 = interpolant("bs1", "bspline", {g1}, v1);
+        // (cubic in both directions: the derivative of a degree-1 spline is a degree-0 one, for which the reference itself writes
+        // boor[degree-1] out of bounds at a knot)
+        Function B2 = interpolant("bs2", "bspline", g2, v2);
+        MX y1 = B1(std::vector<MX>{a}).at(0), y2 = B2(std::vector<MX>{c}).at(0);
+        outs = {y1 * y2(0), y2 + a, cos(y1)};
+      } else if (which == 1) {
+        // a node with its own knot vector (a repeated interior knot) and two values per point
+        std::vector<std::vector<double>> kn = {{0, 0, 0, 0.3, 0.3, 0.7, 1, 1, 1}};
+        std::vector<double> co;
+        for (int i = 0; i < 12; ++i) co.push_back(std::sin(0.7 * i) - 0.2 * i);
+        outs = {MX::bspline(a, DM(co), kn, std::vector<casadi_int>{2}, 2, Dict()), a * a};
+      } else {
+        // parametric coefficients
+        std::vector<std::vector<double>> kn = {{-1, -1, -1, -1, 0, 1, 1, 1, 1}};
+        ins.push_back(cf);
+        outs = {MX::bspline(a, cf, kn, std::vector<casadi_int>{3}, 1, Dict()) + c(0)};
+        outs.at(0) = outs.at(0) + 0 * cf(0);
+      }
+      Function f("bs_case" + str(which), ins, outs);
+      std::vector<Function> fs = {f, f.forward(1), f.reverse(1), f.jacobian()};
+      for (const Function& d : fs) {
+        const casadi_int nn = 40;
+        Function ref = d.map(nn, "serial");
+        auto vin = random_inputs(ref, 91 + which, which == 0 ? -1.2 : -0.2, which == 0 ? 2.2 : 1.2);
+        const double sp0[] = {-1, -0.5, 0, 0.25, 2, -1.25, 2.5, 0.75, 1.5, -0.0, 0.3, 0.7, 1, 1.0000001};
+        for (casadi_int i = 0; i < 14; ++i) vin[0][i] = sp0[i];
+        const double sp1[] = {0, -1, 0.5, 0, 4, 3.5, 5, 4, -1, -2, 2, 1, 4, -1, 0, 3.5};
+        for (casadi_int i = 0; i < 16; ++i) vin[1][20 + i] = sp1[i];
+        try {
+          check_bits(eval_tape(CudaMap::lowered_tape(d), nn, vin), eval(ref, vin), "B-splines, case " + str(which) + ": " + d.name());
+          ++cases;
+        } catch (std::exception& e) {
+          CHECK(false, "B-splines, case " + str(which) + ": " + d.name() + " was refused: " + e.what());
+        }
+      }
+    }
+    printf("B-splines (interpolants, nodes with constant and parametric coefficients) and their derivative functions: %d functions lowered\n", cases);
+  }
   // still refused, loudly: nodes without a numeric evaluation in the reference, side effects
   {
     bool threw = false;
