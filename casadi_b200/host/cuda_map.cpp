@@ -410,6 +410,32 @@ namespace casadi {
             }
             if (o == OP_NORMF) r = op(OP_SQRT, r);
             w[out.at(0)] = Vals(1, r);
+          } else if (o == OP_LOGSUMEXP) {
+            // casadi_logsumexp (runtime/casadi_logsumexp.hpp): "max" is the last x[i] that exceeds x[0] (sic: the reference
+            // compares with x[0], not with the running maximum), the sum skips that element, log1p(sum) + max.  The arg-max
+            // is data: one-hot flags and selects.  (LogSumExp has no eval_sx; its numeric evaluation is replayed here.)
+            const Vals& a = W(in.at(0));
+            const casadi_int nn = static_cast<casadi_int>(a.size());
+            casadi_assert(nn >= 1, "Map 'cuda': logsumexp of an empty operand");
+            ccu_int r = a[0];
+            if (nn > 1) {
+              const ccu_int zero = cst(0.);
+              auto sel = [&](ccu_int c, ccu_int p, ccu_int q) {
+                ccu_int h = lib.builder_select(b, c, p, q);
+                casadi_assert(h >= 0, "Map 'cuda': " + std::string(lib.last_error()));
+                return h;
+              };
+              Vals gt(nn, zero), is_max(nn, zero);
+              ccu_int mx = a[0];
+              for (casadi_int i = 1; i < nn; ++i) { gt[i] = op(OP_LT, a[0], a[i]); mx = sel(gt[i], a[i], mx); }
+              ccu_int later = zero;  // some j > i exceeds x[0]
+              for (casadi_int i = nn; i-- > 1; ) { is_max[i] = op(OP_AND, gt[i], op(OP_NOT, later)); later = op(OP_OR, later, gt[i]); }
+              is_max[0] = op(OP_NOT, later);
+              ccu_int sum = zero;
+              for (casadi_int i = 0; i < nn; ++i) sum = sel(is_max[i], sum, op(OP_ADD, sum, op(OP_EXP, op(OP_SUB, a[i], mx))));
+              r = op(OP_ADD, op(OP_LOG1P, sum), mx);
+            }
+            w[out.at(0)] = Vals(1, r);
           } else if (o == OP_BILIN) {
             // casadi_bilin (runtime/casadi_bilin.hpp): ret = 0; ret += x[rr]*A[el]*y[cc] column by column
             const Vals &A = W(in.at(0)), &xx = W(in.at(1)), &yy = W(in.at(2));

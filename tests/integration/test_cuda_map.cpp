@@ -105,11 +105,11 @@ static void host_side_checks() {
   try { ff.map(4, "cuda"); } catch (std::exception& e) { threw = std::string(e.what()).find("free variables") != std::string::npos; }
   CHECK(threw, "free variables must be rejected at creation");
   // an MX function that can neither be expanded (Linsol call) nor lowered node by node
-  // (logsumexp has no eval_sx to replay and no device lowering) fails loudly at creation: no fallback
+  // (monitor prints: a side effect without a device lowering) fails loudly at creation: no fallback
   {
     Sparsity sp = kkt_sparsity();
     MX K = MX::sym("K", sp), b = MX::sym("b", 60);
-    Function g("g", {K, b}, {solve(K, b, "ldl"), logsumexp(b)});
+    Function g("g", {K, b}, {solve(K, b, "ldl"), b.monitor("b")});
     threw = false;
     try { g.map(4, "cuda"); } catch (std::exception& e) { threw = std::string(e.what()).find("no device lowering") != std::string::npos; }
     CHECK(threw, "MX function with an unsupported node must be rejected");
@@ -165,6 +165,8 @@ static void mx_vocabulary_checks() {
   check("dense", {K, b, M}, {mtimes(M, x), mtimes(x.T(), M.T()), mtimes(densify(K), x), mtimes(K.T(), x), dot(x, b), norm_2(x),
                             sumsqr(x), bilin(K, x, b), mmax(x), mmin(K), mmin(x), norm_inf(x), norm_1(x), norm_fro(K),
                             norm_inf(K), norm_1(M)}, 41);
+  // logsumexp (numeric evaluation only in the reference; its arg-max is data)
+  check("logsumexp", {K, b}, {logsumexp(x), logsumexp(b), logsumexp(x(0)), logsumexp(vertcat(b(0), b(0), x(1)))}, 42);
   // projections, rank-1 update, casts
   check("project", {K, b, al}, {project(K, Sparsity::diag(6)), project(x, Sparsity::dense(6, 1)), rank1(densify(K), al, x, b),
                                 sparsity_cast(x, Sparsity::dense(2, 3)), project(K, Sparsity::dense(6, 6)) - 2 * densify(K)}, 43);
@@ -406,10 +408,6 @@ static void mx_vocabulary_checks() {
     Function h("voc_mon", {K, b}, {x.monitor("x")});
     try { CudaMap::lowered_tape(h); } catch (std::exception& e) { threw = std::string(e.what()).find("no device lowering") != std::string::npos; }
     CHECK(threw, "monitor (a printing side effect) must be refused");
-    threw = false;
-    Function l("voc_lse", {K, b}, {logsumexp(x)});  // (LogSumExp has no eval_sx in the reference: nothing to replay)
-    try { CudaMap::lowered_tape(l); } catch (std::exception& e) { threw = std::string(e.what()).find("no device lowering") != std::string::npos; }
-    CHECK(threw, "logsumexp must be refused");
   }
   printf("MX vocabulary around a Linsol call: dense / projections / nonzeros / AD / embedded maps lowered\n");
 }
