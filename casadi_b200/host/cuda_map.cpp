@@ -410,6 +410,13 @@ namespace casadi {
             }
             if (o == OP_NORMF) r = op(OP_SQRT, r);
             w[out.at(0)] = Vals(1, r);
+          } else if (o == OP_ASSERTION) {
+            // Assertion::eval (assertion.cpp:69-79): the value passes through; the evaluation fails unless the condition is
+            // exactly 1.  An instance that violates it is counted with the failed QR factorisations: the map then fails like
+            // the reference's (whose serial map raises "Assertion error"), instead of dropping the check as an expansion does
+            const ccu_int bad = op(OP_NE, W(in.at(1)).at(0), cst(1.));
+            fail_count = fail_count < 0 ? bad : op(OP_ADD, fail_count, bad);
+            w[out.at(0)] = W(in.at(0));
           } else if (o == OP_LOGSUMEXP) {
             // casadi_logsumexp (runtime/casadi_logsumexp.hpp): "max" is the last x[i] that exceeds x[0] (sic: the reference
             // compares with x[0], not with the running maximum), the sum skips that element, log1p(sum) + max.  The arg-max

@@ -402,6 +402,30 @@ static void mx_vocabulary_checks() {
     }
     printf("B-splines (interpolants, nodes with constant and parametric coefficients) and their derivative functions: %d functions lowered\n", cases);
   }
+  // an assertion next to the solve: the value passes through and a violated condition makes the evaluation fail (the
+  // lowered tape counts the violating instances in its trailing failure output)
+  {
+    Function f("voc_assert", {K, b}, {x.attachAssert(b(0) < 0.5, "b(0) must stay below 0.5") * 2});
+    Function ref = f.map(n, "serial");
+    auto vin = kkt_like_inputs(ref, n, 59);
+    for (casadi_int i = 0; i < n; ++i) vin[1][i * 6] = -0.25;             // every instance satisfies the condition
+    CudaMap::Tape t = CudaMap::lowered_tape(f);
+    auto got = eval_tape(t, n, vin);
+    CHECK(got.size() == 2 && got[1].size() == static_cast<size_t>(n), "the lowered tape must carry a failure count per instance");
+    double bad = 0;
+    for (double v : got[1]) bad += v;
+    CHECK(bad == 0, "no instance violates the assertion");
+    got.resize(1);
+    check_bits(got, eval(ref, vin), "MX vocabulary: assertion (satisfied)");
+    vin[1][3 * 6] = 0.75;                                                  // instance 3 violates it
+    bool threw = false;
+    try { eval(ref, vin); } catch (std::exception& e) { threw = std::string(e.what()).find("Assertion error") != std::string::npos; }
+    CHECK(threw, "the reference's map raises on a violated assertion");
+    got = eval_tape(t, n, vin);
+    bad = 0;
+    for (double v : got[1]) bad += v;
+    CHECK(bad == 1 && got[1][3] == 1, "exactly the violating instance must be counted");
+  }
   // still refused, loudly: nodes without a numeric evaluation in the reference, side effects
   {
     bool threw = false;
