@@ -10,6 +10,7 @@
 #include "rootfinder_impl.hpp"
 #include <casadi/solvers/bspline_interpolant.hpp>  // S_ of the B-spline interpolant (layout only)
 #include <casadi/solvers/linear_interpolant.hpp>  // data members of the lookup-table plugin (layout only; nothing is linked)
+#include <casadi/solvers/fast_newton.hpp>  // option members of the FastNewton plugin class (layout only)
 #include <casadi/solvers/newton.hpp>  // option members of the Newton plugin class (layout only; nothing is linked)
 #include "mx_node.hpp"
 #include "solve.hpp"
@@ -1376,6 +1377,12 @@ namespace casadi {
       static bool line_search(const Newton* p) { return p->*(&NewtonOptions::line_search_); }
     };
 
+    struct FastNewtonOptions : public FastNewton {
+      static casadi_int max_iter(const FastNewton* p) { return p->*(&FastNewtonOptions::max_iter_); }
+      static double abstol(const FastNewton* p) { return p->*(&FastNewtonOptions::abstol_); }
+      static double abstol_step(const FastNewton* p) { return p->*(&FastNewtonOptions::abstolStep_); }
+    };
+
     CudaMap::Tape export_builder(CudaLib& lib, void* b, const std::vector<casadi_int>& nnz_in,
                                  const std::vector<casadi_int>& nnz_out) {
       CudaMap::Tape t;
@@ -1391,7 +1398,7 @@ namespace casadi {
   } // namespace
 
   bool CudaMap::is_newton(const Function& f) {
-    return f.class_name() == "Newton" && dynamic_cast<const Rootfinder*>(f.get()) != nullptr;
+    return (f.class_name() == "Newton" || f.class_name() == "FastNewton") && dynamic_cast<const Rootfinder*>(f.get()) != nullptr;
   }
 
   CudaMap::NewtonPlan CudaMap::newton_plan(const Function& rf) {
@@ -1399,14 +1406,19 @@ namespace casadi {
     CudaLib& lib = cuda_lib();
     casadi_assert(lib.handle!=nullptr, "Map 'cuda': " + lib.error);
     const Rootfinder* R = dynamic_cast<const Rootfinder*>(rf.get());
-    const Newton* Nw = static_cast<const Newton*>(R);
+    // "fast_newton" (casadi/solvers/fast_newton.cpp:140-166 + runtime/casadi_newton.hpp): the same iteration without a line
+    // search, with casadi_qr as its built-in linear solver, norms by casadi_norm_inf (fmax), tolerances that only count when
+    // positive, and the step applied BEFORE it is tested
+    const bool fast = rf.class_name() == "FastNewton";
     NewtonPlan P;
     P.name = rf.name();
     P.n = R->n_; P.iin = R->iin_; P.iout = R->iout_;
-    P.max_iter = NewtonOptions::max_iter(Nw);
-    P.line_search = NewtonOptions::line_search(Nw);
+    P.max_iter = fast ? FastNewtonOptions::max_iter(static_cast<const FastNewton*>(R)) : NewtonOptions::max_iter(static_cast<const Newton*>(R));
+    P.line_search = fast ? false : NewtonOptions::line_search(static_cast<const Newton*>(R));
     P.error_on_fail = R->error_on_fail_;
-    const double abstol = NewtonOptions::abstol(Nw), abstol_step = NewtonOptions::abstol_step(Nw);
+    const double abstol = fast ? FastNewtonOptions::abstol(static_cast<const FastNewton*>(R)) : NewtonOptions::abstol(static_cast<const Newton*>(R));
+    const double abstol_step = fast ? FastNewtonOptions::abstol_step(static_cast<const FastNewton*>(R))
+                                    : NewtonOptions::abstol_step(static_cast<const Newton*>(R));
     const double inf = std::numeric_limits<double>::infinity();
     casadi_assert(P.max_iter >= 1, "Map 'cuda': Newton rootfinder '" + rf.name() + "' with max_iter < 1");
     const casadi_int n = P.n, n_in = rf.n_in(), n_out = rf.n_out();
@@ -1414,7 +1426,8 @@ namespace casadi {
     for (casadi_int j = 0; j < n_out; ++j) { P.nnz_out.push_back(rf.nnz_out(j)); if (j != P.iout) P.aux.push_back(j); }
     casadi_assert(rf.nnz_in(P.iin) == n && rf.nnz_out(P.iout) == n, "Map 'cuda': Newton rootfinder with a sparse unknown");
     const Function& jac = R->get_function("jac_g_x");
-    const Function& g = R->get_function("g");
+    // (fast_newton has no separate residual function; the line-search tape is never launched for it, the oracle fills its place)
+    const Function g = fast ? R->oracle() : R->get_function("g");
     // tape signature (both tapes)
     std::vector<casadi_int> t_in = P.nnz_in, t_out;
     t_in.push_back(n); t_in.push_back(NEWTON_SC);
@@ -1453,7 +1466,12 @@ namespace casadi {
           const Vals& J = r[0];
           const Vals& F = r[1 + P.iout];
           ccu_int abst = zero, conv1 = zero;
-          if (abstol != inf) {
+          if (fast) {
+            if (abstol > 0) {  // casadi_norm_inf(n, g) <= abstol
+              for (casadi_int i = 0; i < n; ++i) abst = L.op(OP_FMAX, abst, L.op(OP_FABS, F[i]));
+              conv1 = L.op(OP_LE, abst, L.cst(abstol));
+            }
+          } else if (abstol != inf) {
             for (casadi_int i = 0; i < n; ++i) {  // abstol = std::max(abstol, fabs(f[i])): (a < b) ? b : a
               ccu_int fa = L.op(OP_FABS, F[i]);
               abst = sel(L.op(OP_LT, abst, fa), fa, abst);
@@ -1461,11 +1479,29 @@ namespace casadi {
             conv1 = L.op(OP_LE, abst, L.cst(abstol));
           }
           Vals dx = F;
-          L.linsol_solve(R->linsol_, J, dx, 1, false);
+          if (fast) {
+            // casadi_qr + casadi_qr_solve on the Jacobian's pattern (FastNewton::init: sp_jac_.qr_sparse, fast_newton.cpp:100)
+            const Sparsity& spj = jac.sparsity_out(0);
+            Sparsity spv, spr;
+            std::vector<casadi_int> prinv, pc;
+            spj.qr_sparse(spv, spr, prinv, pc);
+            std::vector<ccu_int> a1 = Lowering::pattern(spj), v1 = Lowering::pattern(spv), r1 = Lowering::pattern(spr),
+                                 pi(prinv.begin(), prinv.end()), pcc(pc.begin(), pc.end());
+            ccu_int nullity = -1;
+            casadi_assert(lib.builder_qr(L.b, a1.data(), v1.data(), r1.data(), pi.data(), pcc.data(), J.data(), dx.data(), 1, 0, 1e-12,
+                                         &nullity) == 0, "Map 'cuda': " + std::string(lib.last_error()));
+          } else {
+            L.linsol_solve(R->linsol_, J, dx, 1, false);
+          }
           const ccu_int singular = L.fail_count >= 0 ? L.fail_count : zero;
           L.fail_count = -1;
           ccu_int st = zero, conv2 = zero;
-          if (abstol_step != inf) {
+          if (fast) {
+            if (abstol_step > 0) {
+              for (casadi_int i = 0; i < n; ++i) st = L.op(OP_FMAX, st, L.op(OP_FABS, dx[i]));
+              conv2 = L.op(OP_LE, st, L.cst(abstol_step));
+            }
+          } else if (abstol_step != inf) {
             for (casadi_int i = 0; i < n; ++i) {
               ccu_int fa = L.op(OP_FABS, dx[i]);
               st = sel(L.op(OP_LT, st, fa), fa, st);
@@ -1478,7 +1514,8 @@ namespace casadi {
           const ccu_int minus_one = L.cst(-1.);
           for (casadi_int i = 0; i < n; ++i) {
             // without line search: casadi_axpy(n, -alpha, f, x) with alpha = 1
-            Xn[i] = P.line_search ? X[i] : sel(cont, L.op(OP_ADD, X[i], L.op(OP_MUL, minus_one, dx[i])), X[i]);
+            // (fast_newton applies the step whenever the residual test did not stop it, also a step that then ends the iteration)
+            Xn[i] = P.line_search ? X[i] : sel(fast ? upd : cont, L.op(OP_ADD, X[i], L.op(OP_MUL, minus_one, dx[i])), X[i]);
             DXn[i] = sel(upd, dx[i], DX[i]);
           }
           SCn[0] = sel(act, abst, sc_abstol);

@@ -63,6 +63,7 @@ PLUGINS = {
     "interpolant_bspline": ("bspline_interpolant.cpp", "bspline_interpolant_meta.cpp"),
     "integrator_rk": ("runge_kutta.cpp", "runge_kutta_meta.cpp"),
     "rootfinder_newton": ("newton.cpp", "newton_meta.cpp"),
+    "rootfinder_fast_newton": ("fast_newton.cpp", "fast_newton_meta.cpp"),
 }
 
 
@@ -129,7 +130,7 @@ def generate_headers():
         "git_describe": "3.7.2", "feature_list": "\\n * dynamic-loading\\n * openmp\\n * thread",
         "CMAKE_BUILD_TYPE": "Release", "CMAKE_CXX_COMPILER_ID": "GNU",
         "CASADI_CMAKE_CXX_COMPILER": CXX, "CASADI_MODULES": "casadi;" + ";".join("casadi_" + p for p in PLUGINS),
-        "CASADI_PLUGINS": "Linsol::ldl;Linsol::qr;Linsol::tridiag;Linsol::lsqr;Interpolant::linear;Interpolant::bspline;Integrator::rk;Rootfinder::newton", "CASADI_INSTALL_PREFIX": os.path.join(OUT),
+        "CASADI_PLUGINS": "Linsol::ldl;Linsol::qr;Linsol::tridiag;Linsol::lsqr;Interpolant::linear;Interpolant::bspline;Integrator::rk;Rootfinder::newton;Rootfinder::fast_newton", "CASADI_INSTALL_PREFIX": os.path.join(OUT),
         "CMAKE_SHARED_LIBRARY_PREFIX": "lib", "CMAKE_SHARED_LIBRARY_SUFFIX": ".so",
         "CMAKE_C_OUTPUT_EXTENSION": ".o", "casadi_lapack_libraries": "",
     }
