@@ -447,7 +447,7 @@ namespace casadi {
           } else if (o == OP_BILIN) {
             // casadi_bilin (runtime/casadi_bilin.hpp): ret = 0; ret += x[rr]*A[el]*y[cc] column by column
             const Vals &A = W(in.at(0)), &xx = W(in.at(1)), &yy = W(in.at(2));
-            const Sparsity& spA = x.dep(0).sparsity();
+            const Sparsity spA = x.dep(0).sparsity();
             const casadi_int *colind = spA.colind(), *row = spA.row();
             ccu_int r = cst(0.);
             for (casadi_int cc = 0; cc < spA.size2(); ++cc)
