@@ -917,12 +917,17 @@ namespace casadi {
       void call_interpolant(const Function& f, const LinearInterpolant* I, bool grad, const std::vector<const Vals*>& arg,
                             std::vector<Vals*>& res) {
         const std::string who = "Map 'cuda': interpolant '" + f.name() + "': ";
-        casadi_assert(!I->has_parametric_values() && !I->has_parametric_grid(), who + "parametric grids / values have no device lowering");
         casadi_assert(I->batch_x_ == 1, who + "batch_x > 1 has no device lowering");
         const casadi_int ndim = I->ndim_, m = I->m_;
-        const std::vector<double>& grid = I->grid_;
-        const std::vector<double>& values = I->values_;
         const std::vector<casadi_int>& offset = I->offset_;
+        // grid points and table entries: constants of the interpolant, or (the parametric variants, interpolant.hpp:108-146)
+        // operands of the call -- one table per instance of the map
+        const Vals* pgrid = I->has_parametric_grid() ? arg.at(I->arg_grid()) : nullptr;
+        const Vals* pvals = I->has_parametric_values() ? arg.at(I->arg_values()) : nullptr;
+        casadi_assert(!I->has_parametric_grid() || pgrid, who + "the grid operand is missing");
+        casadi_assert(!I->has_parametric_values() || pvals, who + "the values operand is missing");
+        auto gridv = [&](casadi_int e) { return pgrid ? pgrid->at(e) : cst(I->grid_.at(e)); };
+        auto valv = [&](size_t e) { return pvals ? pvals->at(e) : cst(I->values_.at(e)); };
         double work = static_cast<double>(m) * (1 << ndim);
         for (casadi_int i = 0; i < ndim; ++i) work *= static_cast<double>(offset[i + 1] - offset[i]);
         casadi_assert(work <= 2e5, who + "the table is too large to be gathered by selects on the device (" + str(work) + " selects per lookup)");
@@ -938,13 +943,14 @@ namespace casadi {
         Vals alpha(ndim), delta(ndim);
         for (casadi_int i = 0; i < ndim; ++i) {
           const ccu_int xi = arg.at(0) ? arg[0]->at(i) : zero;
-          const double* g = grid.data() + offset[i];
           const casadi_int ng = offset[i + 1] - offset[i];
           casadi_assert(ng >= 2, who + "a grid needs two points");
+          Vals g(ng);
+          for (casadi_int j = 0; j < ng; ++j) g[j] = gridv(offset[i] + j);
           hit[i].assign(ng - 1, zero);
           if (I->lookup_mode_.at(i) == 1) {
             // "exact": j = (casadi_int)((x - g0)*(ng-1)/dg) clamped to [0, ng-2]; trunc(t) >= k  <=>  t >= k for k >= 1
-            const ccu_int t = op(OP_DIV, op(OP_MUL, op(OP_SUB, xi, cst(g[0])), cst(static_cast<double>(ng - 1))), cst(g[ng - 1] - g[0]));
+            const ccu_int t = op(OP_DIV, op(OP_MUL, op(OP_SUB, xi, g[0]), cst(static_cast<double>(ng - 1))), op(OP_SUB, g[ng - 1], g[0]));
             std::vector<ccu_int> ge(ng, zero);  // ge[k] = (t >= k), k = 1 .. ng-2
             for (casadi_int k = 1; k <= ng - 2; ++k) ge[k] = op(OP_LE, cst(static_cast<double>(k)), t);
             for (casadi_int j = 0; j <= ng - 2; ++j) {
@@ -954,14 +960,14 @@ namespace casadi {
           } else {
             // linear / binary search over a strictly increasing grid: the first j in [0, ng-2) with x < g[j+1], else ng-2
             std::vector<ccu_int> lt(ng, zero);  // lt[k] = (x < g[k]), k = 1 .. ng-2
-            for (casadi_int k = 1; k <= ng - 2; ++k) lt[k] = op(OP_LT, xi, cst(g[k]));
+            for (casadi_int k = 1; k <= ng - 2; ++k) lt[k] = op(OP_LT, xi, g[k]);
             for (casadi_int j = 0; j <= ng - 2; ++j) {
               const ccu_int below = j == ng - 2 ? one : lt[j + 1], not_earlier = j == 0 ? one : op(OP_NOT, lt[j]);
               hit[i][j] = op(OP_AND, below, not_earlier);
             }
           }
-          ccu_int gj = cst(g[ng - 2]), gj1 = cst(g[ng - 1]);
-          for (casadi_int j = ng - 2; j-- > 0; ) { gj = sel(hit[i][j], cst(g[j]), gj); gj1 = sel(hit[i][j], cst(g[j + 1]), gj1); }
+          ccu_int gj = g[ng - 2], gj1 = g[ng - 1];
+          for (casadi_int j = ng - 2; j-- > 0; ) { gj = sel(hit[i][j], g[j], gj); gj1 = sel(hit[i][j], g[j + 1], gj1); }
           delta[i] = op(OP_SUB, gj1, gj);
           alpha[i] = op(OP_DIV, op(OP_SUB, xi, gj), delta[i]);
         }
@@ -971,7 +977,7 @@ namespace casadi {
         auto gather = [&](const std::vector<casadi_int>& corner, casadi_int k) {
           // level d holds, for every multi-index of the dimensions >= d, the entry selected in the dimensions < d
           std::vector<ccu_int> cur(static_cast<size_t>(stride[ndim - 1] * ngs[ndim - 1]));
-          for (size_t e = 0; e < cur.size(); ++e) cur[e] = cst(values.at(e * m + k));
+          for (size_t e = 0; e < cur.size(); ++e) cur[e] = valv(e * m + k);
           casadi_int inner = 1;  // entries per block of the dimensions already resolved (always 1 after resolution)
           casadi_int count = static_cast<casadi_int>(cur.size());
           for (casadi_int d = 0; d < ndim; ++d) {

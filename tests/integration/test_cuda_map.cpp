@@ -345,7 +345,38 @@ static void mx_vocabulary_checks() {
         }
       }
     }
-    printf("lookup tables (linear interpolants, three lookup modes) and their derivative functions: %d functions lowered\n", cases);
+    // parametric variants: the table values, the grid, or both are operands -- one table per instance of the map
+    for (int which = 0; which < 3; ++which) {
+      Function L = which == 0 ? interpolant("lutp0", "linear", {g1}, 1)
+                 : which == 1 ? interpolant("lutp1", "linear", std::vector<casadi_int>{7}, v1)
+                              : interpolant("lutp2", "linear", std::vector<casadi_int>{5, 4}, 2);
+      MX a = MX::sym("a", which == 2 ? 2 : 1), gp = MX::sym("gp", which == 2 ? 9 : 7), cp = MX::sym("cp", which == 2 ? 40 : 7);
+      std::vector<MX> largs = {a};
+      if (which >= 1) largs.push_back(gp);
+      if (which != 1) largs.push_back(cp);
+      Function f("lutp_case" + str(which), {a, gp, cp}, {L(largs).at(0) * 2 + gp(0) * cp(0)});
+      for (const Function& d : {f, f.forward(1), f.jacobian()}) {
+        const casadi_int nn = 30;
+        Function ref = d.map(nn, "serial");
+        auto vin = random_inputs(ref, 81 + which, -1.5, 2.5);
+        for (casadi_int i = 0; i < nn; ++i) {  // a strictly increasing grid per instance
+          const casadi_int ngp = which == 2 ? 9 : 7;
+          double acc = -1.0 - 0.01 * static_cast<double>(i);
+          for (casadi_int j = 0; j < ngp; ++j) {
+            if (which == 2 && j == 5) acc = -1.0;
+            acc += 0.2 + 0.05 * static_cast<double>((i + 3 * j) % 7);
+            vin[1][i * ngp + j] = acc;
+          }
+        }
+        try {
+          check_bits(eval_tape(CudaMap::lowered_tape(d), nn, vin), eval(ref, vin), "parametric lookup tables, case " + str(which) + ": " + d.name());
+          ++cases;
+        } catch (std::exception& e) {
+          CHECK(false, "parametric lookup tables, case " + str(which) + ": " + d.name() + " was refused: " + e.what());
+        }
+      }
+    }
+    printf("lookup tables (linear interpolants, three lookup modes, parametric values / grids) and their derivative functions: %d functions lowered\n", cases);
   }
   // B-splines: interpolant(..., "bspline", ...) and MX::bspline nodes (constant and parametric coefficients) -- de Boor's
   // recursion over knots gathered by selects; points inside, on knots, on the ends and outside, and the derivative functions
